@@ -1,0 +1,281 @@
+// Fused gradient-bucket allreduce over NVSwitch peer memory (SURVEY K4/N5/N6 replacement).
+//
+// ONE launch per bucket does, tile by tile:
+//   gather (flatten scattered .grad tensors) -> x scale (1/world) -> cast to wire dtype -> local
+//   symmetric staging -> [peer barrier] -> reduce-scatter (P2P loads from every peer, fp32
+//   accumulate; or multimem.ld_reduce in the switch) -> all-gather (P2P stores to every peer; or
+//   multimem.st) -> [peer barrier] -> cast back -> scatter into .grad / the flat bucket view,
+//   + per-block sum of squares (for clip_grad_norm) + the reduced "parameter used" flags.
+// No NCCL call and no separate elementwise kernel exists on this path.
+//
+// Work ownership is block-local across all phases (block b of every rank touches the same vector
+// set), so only block<->block barriers between GPUs are needed, never a grid-wide one.
+#include "comm_kernels.cuh"
+#include "comm.h"
+
+namespace b200 {
+
+struct ArArgs {
+  CommCtx ctx;
+  size_t stage_off;     // byte offset (in every arena) of this bucket's wire staging region
+  void* flat_out;       // flat bucket in grad dtype (gradient_as_bucket_view) or nullptr
+  float* sq_partials;   // [gridDim.x] or nullptr
+  float* flags_out;     // [count] host-mapped, or nullptr
+  float scale;
+  int scatter;          // write reduced values back into each tensor's own storage
+  BucketTable tab;
+};
+
+template <typename InT, int VE>
+__device__ __forceinline__ void gather_vec(const TensorSlot* slots, const uint32_t* offs, int count,
+                                           uint32_t data_elems, uint32_t e0, float scale, float* f) {
+  if (e0 >= data_elems) {  // "used" flags ride behind the data
+#pragma unroll
+    for (int i = 0; i < VE; ++i) {
+      const uint32_t k = e0 - data_elems + i;
+      f[i] = (k < (uint32_t)count && slots[k].ptr != nullptr) ? 1.f : 0.f;
+    }
+    return;
+  }
+  const int k = find_slot(offs, count, e0);
+  const uint32_t idx = e0 - offs[k];
+  const uint32_t n = slots[k].numel;
+  const InT* src = reinterpret_cast<const InT*>(slots[k].ptr);
+  if (src == nullptr || idx >= n) {
+#pragma unroll
+    for (int i = 0; i < VE; ++i) f[i] = 0.f;
+    return;
+  }
+  src += idx;
+  if (idx + VE <= n && (reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+    if constexpr (sizeof(InT) == 4) {
+#pragma unroll
+      for (int q = 0; q < VE / 4; ++q) {
+        float4 t = __ldg(reinterpret_cast<const float4*>(src) + q);
+        f[4 * q] = t.x * scale; f[4 * q + 1] = t.y * scale; f[4 * q + 2] = t.z * scale; f[4 * q + 3] = t.w * scale;
+      }
+    } else {
+      if constexpr (VE == 8) {
+        uint4 raw = __ldg(reinterpret_cast<const uint4*>(src));
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { float2 t = __bfloat1622float2(h[q]); f[2 * q] = t.x * scale; f[2 * q + 1] = t.y * scale; }
+      } else {
+        uint2 raw = __ldg(reinterpret_cast<const uint2*>(src));
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) { float2 t = __bfloat1622float2(h[q]); f[2 * q] = t.x * scale; f[2 * q + 1] = t.y * scale; }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < VE; ++i) f[i] = (idx + i < n) ? to_f32<InT>(src[i]) * scale : 0.f;
+  }
+}
+
+template <typename InT, int VE>
+__device__ __forceinline__ float deliver_vec(const ArArgs& a, const TensorSlot* slots, const uint32_t* offs,
+                                             uint32_t e0, const float* f) {
+  const int count = a.tab.count;
+  if (e0 >= a.tab.data_elems) {
+    if (a.flags_out != nullptr) {
+#pragma unroll
+      for (int i = 0; i < VE; ++i) {
+        const uint32_t k = e0 - a.tab.data_elems + i;
+        if (k < (uint32_t)count) a.flags_out[k] = f[i];
+      }
+    }
+    return 0.f;
+  }
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < VE; ++i) sq += f[i] * f[i];
+  if (a.flat_out != nullptr) {
+    InT* dst = reinterpret_cast<InT*>(a.flat_out) + e0;   // slots are 8-element aligned: always vectorisable
+    if constexpr (sizeof(InT) == 4) {
+#pragma unroll
+      for (int q = 0; q < VE / 4; ++q)
+        reinterpret_cast<float4*>(dst)[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+    } else {
+      __nv_bfloat162 h[VE / 2];
+#pragma unroll
+      for (int q = 0; q < VE / 2; ++q) h[q] = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
+      if constexpr (VE == 8) *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<uint4*>(h);
+      else *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<uint2*>(h);
+    }
+  }
+  if (a.scatter) {
+    const int k = find_slot(offs, count, e0);
+    const uint32_t idx = e0 - offs[k];
+    const uint32_t n = slots[k].numel;
+    InT* dst = reinterpret_cast<InT*>(slots[k].ptr);
+    if (dst != nullptr && idx < n) {
+      dst += idx;
+      if (idx + VE <= n && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+        if constexpr (sizeof(InT) == 4) {
+#pragma unroll
+          for (int q = 0; q < VE / 4; ++q)
+            reinterpret_cast<float4*>(dst)[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+        } else {
+          __nv_bfloat162 h[VE / 2];
+#pragma unroll
+          for (int q = 0; q < VE / 2; ++q) h[q] = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
+          if constexpr (VE == 8) *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<uint4*>(h);
+          else *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<uint2*>(h);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < VE; ++i)
+          if (idx + i < n) dst[i] = from_f32<InT>(f[i]);
+      }
+    }
+  }
+  return sq;
+}
+
+template <typename InT, typename WireT, int ALGO>
+__global__ void __launch_bounds__(kCommThreads, 1) bucket_allreduce_kernel(const __grid_constant__ ArArgs a) {
+  using W = Wire<WireT>;
+  constexpr int VE = W::VE;
+  __shared__ TensorSlot slots[kMaxBucketTensors];
+  __shared__ uint32_t offs[kMaxBucketTensors + 1];
+  __shared__ float red[33];
+
+  const CommCtx& c = a.ctx;
+  const int P = c.world, r = c.rank, count = a.tab.count;
+  for (int i = threadIdx.x; i < count; i += blockDim.x) { slots[i] = a.tab.t[i]; offs[i] = a.tab.t[i].off; }
+  if (threadIdx.x == 0) offs[count] = a.tab.data_elems;
+  __syncthreads();
+
+  const uint32_t V = a.tab.total_elems / VE;
+  const uint32_t Vs = (V + P - 1) / P;
+  const uint32_t step = gridDim.x * blockDim.x;
+  const uint32_t first = blockIdx.x * blockDim.x + threadIdx.x;
+  char* const my_stage = c.base + (size_t)r * c.stride + a.stage_off;
+  float sq = 0.f;
+
+  // ---- phase 1: gather + scale + cast into local symmetric staging
+  for (int s = 0; s < P; ++s) {
+    for (uint32_t j = first; j < Vs; j += step) {
+      const uint32_t v = (uint32_t)s * Vs + j;
+      if (v >= V) break;
+      float f[VE];
+      gather_vec<InT, VE>(slots, offs, count, a.tab.data_elems, v * VE, a.scale, f);
+      *reinterpret_cast<Vec16*>(my_stage + (size_t)v * 16) = W::pack(f);
+    }
+  }
+  peer_block_barrier(c);
+
+  if constexpr (ALGO == kAlgoOneShot) {
+    // ---- every rank pulls every vector from every peer and reduces locally
+    for (int s = 0; s < P; ++s) {
+      for (uint32_t j = first; j < Vs; j += step) {
+        const uint32_t v = (uint32_t)s * Vs + j;
+        if (v >= V) break;
+        Vec16 x[kMaxRanks];
+#pragma unroll
+        for (int p = 0; p < kMaxRanks; ++p)
+          if (p < P) x[p] = ld_sys(c.base + (size_t)p * c.stride + a.stage_off + (size_t)v * 16);
+        float acc[VE];
+#pragma unroll
+        for (int i = 0; i < VE; ++i) acc[i] = 0.f;
+#pragma unroll
+        for (int p = 0; p < kMaxRanks; ++p)
+          if (p < P) {
+            float f[VE];
+            W::unpack(x[p], f);
+#pragma unroll
+            for (int i = 0; i < VE; ++i) acc[i] += f[i];
+          }
+        // round through the wire format so every algorithm yields the same values
+        Vec16 packed = W::pack(acc);
+        W::unpack(packed, acc);
+        sq += deliver_vec<InT, VE>(a, slots, offs, v * VE, acc);
+      }
+    }
+    peer_block_barrier(c);   // nobody may repack its staging while a peer still reads it
+  } else {
+    // ---- phase 2: reduce-scatter my slice, then all-gather it to every peer
+    for (uint32_t j = first; j < Vs; j += step) {
+      const uint32_t v = (uint32_t)r * Vs + j;
+      if (v >= V) break;
+      const size_t byte_off = a.stage_off + (size_t)v * 16;
+      if constexpr (ALGO == kAlgoNvls) {
+        Vec16 red16 = W::mc_reduce(c.mc_base + byte_off);
+        multimem_st(c.mc_base + byte_off, red16);
+      } else {
+        Vec16 x[kMaxRanks];
+#pragma unroll
+        for (int p = 0; p < kMaxRanks; ++p)
+          if (p < P) x[p] = ld_sys(c.base + (size_t)p * c.stride + byte_off);
+        float acc[VE];
+#pragma unroll
+        for (int i = 0; i < VE; ++i) acc[i] = 0.f;
+#pragma unroll
+        for (int p = 0; p < kMaxRanks; ++p)
+          if (p < P) {
+            float f[VE];
+            W::unpack(x[p], f);
+#pragma unroll
+            for (int i = 0; i < VE; ++i) acc[i] += f[i];
+          }
+        const Vec16 out = W::pack(acc);
+#pragma unroll
+        for (int p = 0; p < kMaxRanks; ++p)
+          if (p < P) st_sys(c.base + (size_t)p * c.stride + byte_off, out);
+      }
+    }
+    peer_block_barrier(c);
+    // ---- phase 3: cast back + scatter from local staging
+    for (int s = 0; s < P; ++s) {
+      for (uint32_t j = first; j < Vs; j += step) {
+        const uint32_t v = (uint32_t)s * Vs + j;
+        if (v >= V) break;
+        float f[VE];
+        W::unpack(ld_cg(my_stage + (size_t)v * 16), f);
+        sq += deliver_vec<InT, VE>(a, slots, offs, v * VE, f);
+      }
+    }
+  }
+
+  if (a.sq_partials != nullptr) {
+    const float total = block_sum(sq, red);
+    if (threadIdx.x == 0) a.sq_partials[blockIdx.x] = total;
+  }
+}
+
+template <typename InT, typename WireT>
+static void launch_typed(const ArArgs& args, int algo, int blocks, cudaStream_t stream) {
+  switch (algo) {
+    case kAlgoOneShot: bucket_allreduce_kernel<InT, WireT, kAlgoOneShot><<<blocks, kCommThreads, 0, stream>>>(args); break;
+    case kAlgoTwoShot: bucket_allreduce_kernel<InT, WireT, kAlgoTwoShot><<<blocks, kCommThreads, 0, stream>>>(args); break;
+    case kAlgoNvls:    bucket_allreduce_kernel<InT, WireT, kAlgoNvls><<<blocks, kCommThreads, 0, stream>>>(args); break;
+    default: throw std::runtime_error("bucket_allreduce: unknown algorithm");
+  }
+}
+
+void launch_bucket_allreduce(const CommCtx& ctx, const BucketTable& tab, size_t stage_off, DType in_dtype,
+                             DType wire_dtype, int algo, int blocks, void* flat_out, float* sq_partials,
+                             float* flags_out, float scale, bool scatter, cudaStream_t stream) {
+  if (blocks < 1 || blocks > kMaxCommBlocks) throw std::runtime_error("bucket_allreduce: bad block count");
+  if (algo == kAlgoNvls && ctx.mc_base == nullptr) throw std::runtime_error("bucket_allreduce: NVLS requested without multicast");
+  if (tab.total_elems % 8 != 0) throw std::runtime_error("bucket_allreduce: bucket not padded to 8 elements");
+  ArArgs args;
+  args.ctx = ctx;
+  args.stage_off = stage_off;
+  args.flat_out = flat_out;
+  args.sq_partials = sq_partials;
+  args.flags_out = flags_out;
+  args.scale = scale;
+  args.scatter = scatter ? 1 : 0;
+  args.tab = tab;
+  const bool in_bf16 = in_dtype == DType::BF16, wire_bf16 = wire_dtype == DType::BF16;
+  if (in_dtype != DType::BF16 && in_dtype != DType::F32) throw std::runtime_error("bucket_allreduce: grads must be fp32 or bf16");
+  if (in_bf16 && wire_bf16) launch_typed<__nv_bfloat16, __nv_bfloat16>(args, algo, blocks, stream);
+  else if (in_bf16) launch_typed<__nv_bfloat16, float>(args, algo, blocks, stream);
+  else if (wire_bf16) launch_typed<float, __nv_bfloat16>(args, algo, blocks, stream);
+  else launch_typed<float, float>(args, algo, blocks, stream);
+  B200_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace b200

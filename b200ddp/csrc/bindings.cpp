@@ -1,0 +1,405 @@
+// Python bindings.  The only translation unit that sees torch headers.
+#include <torch/extension.h>
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+
+#include "comm.h"
+#include "comm_kernels.cuh"
+#include "gemm.h"
+#include "ops.h"
+#include "peer_mem.h"
+#include "reducer.h"
+
+namespace py = pybind11;
+using namespace b200;
+
+namespace {
+
+DType dtype_of(const at::Tensor& t) {
+  switch (t.scalar_type()) {
+    case at::kFloat: return DType::F32;
+    case at::kBFloat16: return DType::BF16;
+    case at::kByte: return DType::U8;
+    case at::kLong: return DType::I64;
+    default: throw std::runtime_error("b200ddp: unsupported dtype " + std::string(c10::toString(t.scalar_type())));
+  }
+}
+
+cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
+
+void check_cuda(const at::Tensor& t, const char* name) {
+  TORCH_CHECK(t.is_cuda(), name, " must be a CUDA tensor");
+  TORCH_CHECK(t.is_contiguous() || t.is_non_overlapping_and_dense(), name, " must be dense");
+}
+
+CommCtx make_ctx(PeerArena& a, size_t pad_off, double timeout_s) {
+  CommCtx c;
+  c.base = a.base();
+  c.mc_base = a.mc_base();
+  c.stride = a.stride();
+  c.pad_off = pad_off;
+  c.error_word = a.error_word_dev();
+  c.timeout_ns = (unsigned long long)(timeout_s * 1e9);
+  c.rank = a.rank();
+  c.world = a.world();
+  return c;
+}
+
+// Standalone fused allreduce of a list of tensors treated as one flat bucket (tests, sweeps,
+// PeerCollectives.allreduce_).  Slots are padded to 8 elements, a flags tail is appended.
+void allreduce_tensors(PeerArena& arena, const std::vector<at::Tensor>& tensors, const std::string& wire, int algo,
+                       int blocks, size_t stage_off, size_t stage_bytes, double scale, int pad_set, double timeout_s,
+                       c10::optional<at::Tensor> sq_partials) {
+  TORCH_CHECK(!tensors.empty() && (int)tensors.size() <= kMaxBucketTensors, "allreduce_tensors: 1..", kMaxBucketTensors, " tensors");
+  const DType in_dt = dtype_of(tensors[0]);
+  const DType wire_dt = wire == "fp32" ? DType::F32 : DType::BF16;
+  BucketTable tab;
+  uint32_t off = 0;
+  tab.count = (int)tensors.size();
+  for (int k = 0; k < tab.count; ++k) {
+    const at::Tensor& t = tensors[k];
+    check_cuda(t, "tensor");
+    TORCH_CHECK(dtype_of(t) == in_dt, "allreduce_tensors: mixed dtypes in one bucket");
+    tab.t[k].ptr = t.data_ptr();
+    tab.t[k].numel = (uint32_t)t.numel();
+    tab.t[k].off = off;
+    off += (uint32_t)((t.numel() + 7) / 8 * 8);
+  }
+  tab.data_elems = off;
+  tab.total_elems = off + (uint32_t)((tab.count + 7) / 8 * 8);
+  tab._pad = 0;
+  TORCH_CHECK((size_t)tab.total_elems * dtype_size(wire_dt) <= stage_bytes, "allreduce_tensors: staging region too small");
+  CommCtx ctx = make_ctx(arena, (size_t)pad_set * kMaxCommBlocks * kMaxRanks * sizeof(uint32_t), timeout_s);
+  if (algo == kAlgoAuto) algo = arena.has_multicast() ? kAlgoNvls : kAlgoTwoShot;
+  float* sq = sq_partials.has_value() ? sq_partials->data_ptr<float>() : nullptr;
+  launch_bucket_allreduce(ctx, tab, stage_off, in_dt, wire_dt, algo, blocks, nullptr, sq, nullptr, (float)scale,
+                          /*scatter=*/true, cur_stream());
+}
+
+// Broadcast arbitrary tensors from `src`; chunked through the staging region.
+int broadcast_tensors(PeerArena& arena, const std::vector<at::Tensor>& tensors, int src, size_t stage_off,
+                      size_t stage_bytes, bool use_mc, int blocks, int pad_set, double timeout_s) {
+  CommCtx ctx = make_ctx(arena, (size_t)pad_set * kMaxCommBlocks * kMaxRanks * sizeof(uint32_t), timeout_s);
+  int launches = 0;
+  size_t i = 0;
+  const size_t n = tensors.size();
+  // a tensor larger than the staging region is sent in pieces
+  size_t piece_off = 0;
+  while (i < n) {
+    BucketTable tab;
+    tab.count = 0;
+    uint32_t off = 0;
+    while (i < n && tab.count < kMaxBucketTensors) {
+      const at::Tensor& t = tensors[i];
+      check_cuda(t, "tensor");
+      const size_t nbytes = (size_t)t.numel() * t.element_size() - piece_off;
+      const size_t room = stage_bytes - off;
+      if (room < 16) break;
+      size_t take = nbytes <= room ? nbytes : (room / 16) * 16;
+      if (take == 0) break;
+      tab.t[tab.count].ptr = static_cast<char*>(t.data_ptr()) + piece_off;
+      tab.t[tab.count].numel = (uint32_t)take;
+      tab.t[tab.count].off = off;
+      ++tab.count;
+      off += (uint32_t)((take + 15) / 16 * 16);
+      if (take == nbytes) { ++i; piece_off = 0; } else { piece_off += take; break; }
+    }
+    if (tab.count == 0) throw std::runtime_error("broadcast_tensors: staging region too small");
+    tab.data_elems = off;
+    tab.total_elems = off;
+    tab._pad = 0;
+    launch_peer_broadcast(ctx, tab, stage_off, src, use_mc, blocks, cur_stream());
+    ++launches;
+  }
+  return launches;
+}
+
+// ---- optimizer ---------------------------------------------------------------------------------
+struct SgdPlan {
+  std::vector<uintptr_t> params;
+  std::vector<long long> numels, flat_offs;
+  DType p_dtype, g_dtype;
+  int total_blocks = 0;
+  SgdPlan(std::vector<uintptr_t> p, std::vector<long long> n, std::vector<long long> fo, int pd, int gd)
+      : params(std::move(p)), numels(std::move(n)), flat_offs(std::move(fo)), p_dtype((DType)pd), g_dtype((DType)gd) {
+    for (auto v : numels) total_blocks += ceil_div(v, kOptChunk);
+  }
+  template <typename F>
+  void for_each_table(const std::vector<uintptr_t>& grads, F&& fn) const {
+    size_t i = 0;
+    int block_base = 0;
+    while (i < params.size()) {
+      OptTable tab;
+      tab.count = 0;
+      tab.total_blocks = 0;
+      while (i < params.size() && tab.count < kMaxOptTensors) {
+        OptSlot& s = tab.t[tab.count++];
+        s.p = reinterpret_cast<void*>(params[i]);
+        s.g = reinterpret_cast<const void*>(grads[i]);
+        s.flat_off = (unsigned long long)flat_offs[i];
+        s.numel = (uint32_t)numels[i];
+        s.blk0 = (uint32_t)tab.total_blocks;
+        tab.total_blocks += ceil_div(numels[i], kOptChunk);
+        ++i;
+      }
+      fn(tab, block_base);
+      block_base += tab.total_blocks;
+    }
+  }
+  int sqnorm(const std::vector<uintptr_t>& grads, uintptr_t partials, uintptr_t stream) const {
+    TORCH_CHECK(grads.size() == params.size(), "SgdPlan: gradient list length mismatch");
+    for_each_table(grads, [&](const OptTable& tab, int base) {
+      launch_multi_sqnorm(tab, g_dtype, reinterpret_cast<float*>(partials) + base, reinterpret_cast<cudaStream_t>(stream));
+    });
+    return total_blocks;
+  }
+  void step(const std::vector<uintptr_t>& grads, uintptr_t lr, uintptr_t clip_coef, uintptr_t master, uintptr_t mom,
+            uintptr_t step_count, double momentum, double dampening, double weight_decay, double grad_scale, bool nesterov,
+            bool zero_grad, uintptr_t stream) const {
+    TORCH_CHECK(grads.size() == params.size(), "SgdPlan: gradient list length mismatch");
+    SgdHyper h;
+    h.lr = reinterpret_cast<const float*>(lr);
+    h.clip_coef = reinterpret_cast<const float*>(clip_coef);
+    h.master = reinterpret_cast<float*>(master);
+    h.momentum_buf = reinterpret_cast<float*>(mom);
+    h.step_count = reinterpret_cast<const int*>(step_count);
+    h.momentum = (float)momentum;
+    h.dampening = (float)dampening;
+    h.weight_decay = (float)weight_decay;
+    h.grad_scale = (float)grad_scale;
+    h.nesterov = nesterov ? 1 : 0;
+    h.zero_grad = zero_grad ? 1 : 0;
+    for_each_table(grads, [&](const OptTable& tab, int) {
+      launch_multi_sgd(tab, p_dtype, g_dtype, h, reinterpret_cast<cudaStream_t>(stream));
+    });
+  }
+};
+
+}  // namespace
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.doc() = "b200ddp native extension (sm_100a)";
+  m.attr("MAX_BUCKET_TENSORS") = kMaxBucketTensors;
+  m.attr("MAX_COMM_BLOCKS") = kMaxCommBlocks;
+  m.attr("SIGNAL_BYTES") = (long long)kSignalBytes;
+  m.attr("ALGO_AUTO") = (int)kAlgoAuto;
+  m.attr("ALGO_ONE_SHOT") = (int)kAlgoOneShot;
+  m.attr("ALGO_TWO_SHOT") = (int)kAlgoTwoShot;
+  m.attr("ALGO_NVLS") = (int)kAlgoNvls;
+
+  m.def("assign_by_size", &assign_by_size, py::arg("nbytes"), py::arg("keys"), py::arg("limits"), py::arg("max_tensors") = 0);
+
+  py::class_<PeerArena>(m, "PeerArena")
+      .def(py::init<int, int, int, size_t, const std::string&>())
+      .def("bind_socket", &PeerArena::bind_socket)
+      .def("exchange", &PeerArena::exchange, py::call_guard<py::gil_scoped_release>())
+      .def("multicast_supported", &PeerArena::multicast_supported)
+      .def("multicast_create", &PeerArena::multicast_create, py::call_guard<py::gil_scoped_release>())
+      .def("multicast_add_device", &PeerArena::multicast_add_device)
+      .def("multicast_bind", &PeerArena::multicast_bind)
+      .def("disable_multicast", &PeerArena::disable_multicast)
+      .def("has_multicast", &PeerArena::has_multicast)
+      .def("alloc", &PeerArena::alloc, py::arg("nbytes"), py::arg("align") = 256)
+      .def("used", &PeerArena::used)
+      .def("bytes", &PeerArena::bytes)
+      .def("rank", &PeerArena::rank)
+      .def("world", &PeerArena::world)
+      .def("local_ptr", [](PeerArena& a) { return (uintptr_t)a.local(); })
+      .def("peer_ptr", [](PeerArena& a, int r) { return (uintptr_t)a.peer(r); })
+      .def("mc_ptr", [](PeerArena& a) { return (uintptr_t)a.mc_base(); })
+      .def("check_error", &PeerArena::check_error)
+      .def("clear_error", &PeerArena::clear_error)
+      .def("close", &PeerArena::close);
+
+  m.def("allreduce_tensors", &allreduce_tensors, py::arg("arena"), py::arg("tensors"), py::arg("wire") = "bf16",
+        py::arg("algo") = (int)kAlgoAuto, py::arg("blocks") = 32, py::arg("stage_off"), py::arg("stage_bytes"),
+        py::arg("scale") = 1.0, py::arg("pad_set") = 1, py::arg("timeout_s") = 30.0, py::arg("sq_partials") = py::none());
+  m.def("broadcast_tensors", &broadcast_tensors, py::arg("arena"), py::arg("tensors"), py::arg("src") = 0, py::arg("stage_off"),
+        py::arg("stage_bytes"), py::arg("use_mc") = false, py::arg("blocks") = 32, py::arg("pad_set") = 1,
+        py::arg("timeout_s") = 30.0);
+  m.def("peer_pull", [](PeerArena& a, int peer, size_t src_off, at::Tensor dst, size_t bytes, int blocks) {
+    launch_peer_pull(make_ctx(a, 0, 30.0), peer, src_off, dst.data_ptr(), bytes, blocks, cur_stream());
+  });
+  m.def("peer_push", [](PeerArena& a, int peer, size_t dst_off, at::Tensor src, size_t bytes, int blocks) {
+    launch_peer_push(make_ctx(a, 0, 30.0), peer, dst_off, src.data_ptr(), bytes, blocks, cur_stream());
+  });
+  m.def("peer_barrier", [](PeerArena& a, int blocks, int pad_set, double timeout_s) {
+    launch_peer_barrier(make_ctx(a, (size_t)pad_set * kMaxCommBlocks * kMaxRanks * sizeof(uint32_t), timeout_s), blocks, cur_stream());
+  }, py::arg("arena"), py::arg("blocks") = 1, py::arg("pad_set") = 1, py::arg("timeout_s") = 30.0);
+
+  py::class_<BucketPlan>(m, "BucketPlan")
+      .def(py::init<>())
+      .def_readwrite("param_indices", &BucketPlan::param_indices)
+      .def_readwrite("numels", &BucketPlan::numels)
+      .def_readwrite("offsets", &BucketPlan::offsets)
+      .def_readwrite("data_elems", &BucketPlan::data_elems)
+      .def_readwrite("total_elems", &BucketPlan::total_elems);
+
+  py::class_<Reducer>(m, "Reducer")
+      .def(py::init([](PeerArena& arena, std::vector<BucketPlan> plans, int num_params, int grad_dtype, int wire_dtype, int algo,
+                       int max_blocks, long long one_shot_max_bytes, bool as_view, bool find_unused, double extra_scale,
+                       double timeout_s) {
+             ReducerOptions o;
+             o.grad_dtype = (DType)grad_dtype;
+             o.wire_dtype = (DType)wire_dtype;
+             o.algo = algo;
+             o.max_blocks = max_blocks;
+             o.one_shot_max_bytes = one_shot_max_bytes;
+             o.as_view = as_view;
+             o.find_unused = find_unused;
+             o.extra_scale = (float)extra_scale;
+             o.timeout_s = timeout_s;
+             return std::make_unique<Reducer>(&arena, std::move(plans), num_params, o);
+           }),
+           py::keep_alive<1, 2>())
+      .def("num_buckets", &Reducer::num_buckets)
+      .def("bucket_blocks", &Reducer::bucket_blocks)
+      .def("bucket_algo", &Reducer::bucket_algo)
+      .def("set_flat_out", &Reducer::set_flat_out)
+      .def("set_sq_partials", &Reducer::set_sq_partials)
+      .def("reset", &Reducer::reset)
+      .def("mark_ready", &Reducer::mark_ready)
+      .def("finalize", &Reducer::finalize)
+      .def("read_used_flags", &Reducer::read_used_flags)
+      .def("synchronize", &Reducer::synchronize)
+      .def("comm_stream", &Reducer::comm_stream)
+      .def("error_code", &Reducer::error_code)
+      .def_readonly("launches", &Reducer::launches)
+      .def_readonly("bytes_on_wire", &Reducer::bytes_on_wire)
+      .def_readonly("iterations", &Reducer::iterations)
+      .def_readonly("ready_order", &Reducer::ready_order);
+
+  py::class_<SgdPlan>(m, "SgdPlan")
+      .def(py::init<std::vector<uintptr_t>, std::vector<long long>, std::vector<long long>, int, int>())
+      .def_readonly("total_blocks", &SgdPlan::total_blocks)
+      .def("sqnorm", &SgdPlan::sqnorm)
+      .def("step", &SgdPlan::step);
+  m.def("clip_coef", [](at::Tensor partials, int n, double max_norm, double grad_scale, at::Tensor coef, at::Tensor norm) {
+    launch_clip_coef(partials.data_ptr<float>(), n, (float)max_norm, (float)grad_scale, coef.data_ptr<float>(),
+                     norm.data_ptr<float>(), cur_stream());
+  });
+
+  // ---- losses -----------------------------------------------------------------------------------
+  m.def("mse_fwd_bwd", [](at::Tensor out, at::Tensor target, double gscale) {
+    check_cuda(out, "out"); check_cuda(target, "target");
+    TORCH_CHECK(out.is_contiguous() && target.is_contiguous() && out.sizes() == target.sizes() && out.dtype() == target.dtype(),
+                "mse_fwd_bwd: out/target must be contiguous with equal shape and dtype");
+    c10::cuda::CUDAGuard guard(out.device());
+    const size_t n = (size_t)out.numel();
+    const int blocks = mse_blocks(n);
+    at::Tensor loss = at::empty({}, out.options().dtype(at::kFloat));
+    at::Tensor dout = at::empty_like(out);
+    at::Tensor scratch = at::zeros({blocks + 1}, out.options().dtype(at::kFloat));
+    launch_mse_fwd_bwd(out.data_ptr(), target.data_ptr(), dtype_of(out), n, (float)gscale, loss.data_ptr<float>(), dout.data_ptr(),
+                       scratch.data_ptr<float>(), blocks, cur_stream());
+    return std::make_tuple(loss, dout);
+  });
+  m.def("xent_fwd_bwd", [](at::Tensor logits, at::Tensor targets, long long ignore_index, double gscale) {
+    check_cuda(logits, "logits"); check_cuda(targets, "targets");
+    TORCH_CHECK(logits.dim() == 2 && logits.is_contiguous() && targets.is_contiguous() && targets.scalar_type() == at::kLong &&
+                targets.numel() == logits.size(0), "xent_fwd_bwd: logits [rows, cols] contiguous, targets int64 [rows]");
+    c10::cuda::CUDAGuard guard(logits.device());
+    const int rows = (int)logits.size(0), cols = (int)logits.size(1);
+    at::Tensor loss = at::empty({}, logits.options().dtype(at::kFloat));
+    at::Tensor row_loss = at::empty({rows + 1}, logits.options().dtype(at::kFloat));
+    at::Tensor dlogits = at::empty_like(logits);
+    launch_xent_fwd_bwd(logits.data_ptr(), targets.data_ptr<int64_t>() ? (const long long*)targets.data_ptr<int64_t>() : nullptr,
+                        dtype_of(logits), rows, cols, ignore_index, (float)gscale, row_loss.data_ptr<float>(), loss.data_ptr<float>(),
+                        dlogits.data_ptr(), cur_stream());
+    return std::make_tuple(loss, dlogits);
+  });
+
+  // ---- layer norm -------------------------------------------------------------------------------
+  m.def("layernorm_fwd", [](at::Tensor x, at::Tensor gamma, at::Tensor beta, double eps) {
+    check_cuda(x, "x");
+    TORCH_CHECK(x.is_contiguous() && gamma.is_contiguous() && beta.is_contiguous(), "layernorm_fwd: contiguous inputs");
+    TORCH_CHECK(gamma.dtype() == x.dtype() && beta.dtype() == x.dtype(), "layernorm_fwd: gamma/beta dtype must match x");
+    c10::cuda::CUDAGuard guard(x.device());
+    const int cols = (int)x.size(-1);
+    const int rows = (int)(x.numel() / cols);
+    at::Tensor y = at::empty_like(x);
+    at::Tensor mean = at::empty({rows}, x.options().dtype(at::kFloat));
+    at::Tensor rstd = at::empty({rows}, x.options().dtype(at::kFloat));
+    launch_layernorm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), dtype_of(x), rows, cols, (float)eps, y.data_ptr(),
+                         mean.data_ptr<float>(), rstd.data_ptr<float>(), cur_stream());
+    return std::make_tuple(y, mean, rstd);
+  });
+  m.def("layernorm_bwd", [](at::Tensor dy, at::Tensor x, at::Tensor gamma, at::Tensor mean, at::Tensor rstd) {
+    check_cuda(dy, "dy");
+    TORCH_CHECK(dy.is_contiguous() && x.is_contiguous(), "layernorm_bwd: contiguous inputs");
+    c10::cuda::CUDAGuard guard(x.device());
+    const int cols = (int)x.size(-1);
+    const int rows = (int)(x.numel() / cols);
+    const int parts = layernorm_partial_rows(rows);
+    at::Tensor dx = at::empty_like(x);
+    at::Tensor dgp = at::empty({parts, cols}, x.options().dtype(at::kFloat));
+    at::Tensor dbp = at::empty({parts, cols}, x.options().dtype(at::kFloat));
+    at::Tensor dgamma = at::empty_like(gamma);
+    at::Tensor dbeta = at::empty_like(gamma);
+    launch_layernorm_bwd(dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr<float>(), rstd.data_ptr<float>(), dtype_of(x),
+                         rows, cols, dx.data_ptr(), dgp.data_ptr<float>(), dbp.data_ptr<float>(), parts, dgamma.data_ptr(),
+                         dbeta.data_ptr(), cur_stream());
+    return std::make_tuple(dx, dgamma, dbeta);
+  });
+
+  // ---- linears ----------------------------------------------------------------------------------
+  m.def("small_linear_fwd", [](at::Tensor x, at::Tensor w, c10::optional<at::Tensor> b, bool relu) {
+    check_cuda(x, "x");
+    TORCH_CHECK(x.scalar_type() == at::kFloat && w.scalar_type() == at::kFloat && x.is_contiguous() && w.is_contiguous(),
+                "small_linear_fwd: fp32 contiguous");
+    c10::cuda::CUDAGuard guard(x.device());
+    const int K = (int)x.size(-1), N = (int)w.size(0);
+    const int M = (int)(x.numel() / K);
+    auto sizes = x.sizes().vec();
+    sizes.back() = N;
+    at::Tensor y = at::empty(sizes, x.options());
+    launch_small_linear_fwd(x.data_ptr<float>(), w.data_ptr<float>(), b.has_value() ? b->data_ptr<float>() : nullptr,
+                            y.data_ptr<float>(), M, N, K, relu ? 1 : 0, cur_stream());
+    return y;
+  });
+  m.def("small_linear_bwd", [](at::Tensor dy, at::Tensor x, at::Tensor w, at::Tensor y, bool relu, bool need_dx, bool has_bias) {
+    check_cuda(dy, "dy");
+    c10::cuda::CUDAGuard guard(x.device());
+    const int K = (int)x.size(-1), N = (int)w.size(0);
+    const int M = (int)(x.numel() / K);
+    at::Tensor dyc = dy.contiguous();
+    at::Tensor dx = need_dx ? at::empty_like(x) : at::Tensor();
+    at::Tensor dw = at::empty_like(w);
+    at::Tensor db = has_bias ? at::empty({N}, w.options()) : at::Tensor();
+    launch_small_linear_bwd(dyc.data_ptr<float>(), x.data_ptr<float>(), w.data_ptr<float>(), y.data_ptr<float>(),
+                            need_dx ? dx.data_ptr<float>() : nullptr, dw.data_ptr<float>(), has_bias ? db.data_ptr<float>() : nullptr,
+                            M, N, K, relu ? 1 : 0, 0, cur_stream());
+    return std::make_tuple(dx, dw, db);
+  });
+
+  // tcgen05 GEMM: D[M,N] = act(A[M,K] @ B[N,K]^T + bias) ; all bf16 row-major, fp32 accumulate in TMEM
+  m.def("gemm_nt", [](at::Tensor a, at::Tensor b, c10::optional<at::Tensor> bias, int epilogue, c10::optional<at::Tensor> out) {
+    check_cuda(a, "a"); check_cuda(b, "b");
+    TORCH_CHECK(a.scalar_type() == at::kBFloat16 && b.scalar_type() == at::kBFloat16, "gemm_nt: bf16 operands");
+    TORCH_CHECK(a.dim() == 2 && b.dim() == 2 && a.size(1) == b.size(1) && a.is_contiguous() && b.is_contiguous(),
+                "gemm_nt: A [M,K], B [N,K], both K-major contiguous");
+    c10::cuda::CUDAGuard guard(a.device());
+    const int M = (int)a.size(0), K = (int)a.size(1), N = (int)b.size(0);
+    at::Tensor d = out.has_value() ? *out : at::empty({M, N}, a.options());
+    TORCH_CHECK(d.is_contiguous() && d.size(0) == M && d.size(1) == N, "gemm_nt: bad output");
+    const void* bias_ptr = nullptr;
+    if (bias.has_value()) {
+      TORCH_CHECK(bias->scalar_type() == at::kBFloat16 && bias->numel() == N, "gemm_nt: bias bf16 [N]");
+      bias_ptr = bias->data_ptr();
+    }
+    launch_gemm_nt_bf16(a.data_ptr(), b.data_ptr(), d.data_ptr(), bias_ptr, M, N, K, epilogue, dtype_of(d), cur_stream());
+    return d;
+  }, py::arg("a"), py::arg("b"), py::arg("bias") = py::none(), py::arg("epilogue") = 0, py::arg("out") = py::none());
+  m.def("gemm_supported", &gemm_shape_supported);
+
+  // ---- input pipeline ---------------------------------------------------------------------------
+  m.def("normalize_to_channels_last", [](at::Tensor src, at::Tensor dst, at::Tensor mean, at::Tensor inv_std, double in_scale) {
+    check_cuda(src, "src"); check_cuda(dst, "dst");
+    TORCH_CHECK(src.dim() == 4 && src.is_contiguous(), "normalize_to_channels_last: src NCHW contiguous");
+    TORCH_CHECK(dst.is_contiguous(at::MemoryFormat::ChannelsLast) && dst.sizes() == src.sizes(), "normalize_to_channels_last: dst channels_last");
+    c10::cuda::CUDAGuard guard(src.device());
+    launch_normalize_to_channels_last(src.data_ptr(), dtype_of(src), dst.data_ptr(), dtype_of(dst), (int)src.size(0), (int)src.size(1),
+                                      (int)src.size(2), (int)src.size(3), mean.data_ptr<float>(), inv_std.data_ptr<float>(),
+                                      (float)in_scale, cur_stream());
+  });
+}

@@ -1,0 +1,425 @@
+// bf16 GEMM on the 5th-gen tensor cores (SURVEY N9/G1/G3/G5 replacement for the cuBLASLt calls behind
+// nn.Linear forward / dgrad / wgrad).
+//
+//   D[M,N] = epilogue( sum_k A[m,k] * B[n,k] )        fp32 accumulation in TMEM
+//
+// Hand-written for sm_100a: TMA (cp.async.bulk.tensor) stages 128B-swizzled operand tiles into shared
+// memory, ONE elected thread issues tcgen05.mma (cta_group::1, M=128 x N=BLOCK_N x K=16 atoms) into a
+// double-buffered TMEM accumulator, tcgen05.commit arrives on mbarriers to recycle smem stages and to
+// hand finished tiles to the epilogue warps, which read TMEM with tcgen05.ld, apply bias/ReLU/GELU and
+// store bf16/fp32.  Persistent: one CTA per SM walks tiles m-fastest so CTAs running concurrently share
+// the same B tile in L2.
+//
+// Operand majorness (so backward needs no transposes):
+//   A "K-major"  : A stored [M, K] row-major   (forward x, dgrad dy)
+//   A "MN-major" : A stored [K, M] row-major   (wgrad: dy^T)
+//   B "K-major"  : B stored [N, K] row-major   (forward W)
+//   B "MN-major" : B stored [K, N] row-major   (dgrad W, wgrad x)
+#include "gemm.h"
+
+#include <cuda.h>
+#include <mutex>
+#include <unordered_map>
+
+#include "drv.h"
+
+namespace b200 {
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;          // 64 bf16 = 128 bytes = one swizzle-128B row
+constexpr int UMMA_K = 16;
+constexpr int kNumEpilogueWarps = 4;
+constexpr int kNumThreads = 128 + kNumEpilogueWarps * 32;   // warps 0..3: TMA, MMA, TMEM-alloc, idle; 4..7 epilogue
+constexpr int kAccumStages = 2;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}"
+      ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* smem, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// Shared-memory matrix descriptor, 128B swizzle (layout_type 2), descriptor version 1 (Blackwell).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);            // [0,14)  start address >> 4
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;        // [16,30) leading byte offset >> 4
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;        // [32,46) stride byte offset >> 4
+  d |= (uint64_t)1 << 46;                                  // [46,48) version = 1
+  d |= (uint64_t)2 << 61;                                  // [61,64) SWIZZLE_128B
+  return d;
+}
+
+// Instruction descriptor for kind::f16, bf16 x bf16 -> fp32.
+__host__ __device__ constexpr uint32_t make_idesc(int umma_m, int umma_n, bool a_mn, bool b_mn) {
+  return (1u << 4)                       // c_format  = F32
+         | (1u << 7)                     // a_format  = BF16
+         | (1u << 10)                    // b_format  = BF16
+         | ((a_mn ? 1u : 0u) << 15)      // a_major   (0 = K, 1 = MN)
+         | ((b_mn ? 1u : 0u) << 16)      // b_major
+         | ((uint32_t)(umma_n >> 3) << 17)
+         | ((uint32_t)(umma_m >> 4) << 24);
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+
+struct GemmParams {
+  int M, N, K;
+  int epilogue;           // 0 none, 1 +bias, 2 +bias,relu, 3 +bias,gelu(erf)
+  int out_fp32;
+  int accumulate;         // D += result (fp32 output only; gradient accumulation)
+  void* d;
+  const __nv_bfloat16* bias;
+};
+
+template <int BLOCK_N, bool A_MN, bool B_MN>
+struct SmemLayout {
+  static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
+  static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int kBarrierBytes = 1024;
+  static constexpr int kTotal = kStages * kStageBytes + kBarrierBytes + 1024 /*alignment slack*/;
+};
+
+template <int BLOCK_N, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmParams p) {
+  using L = SmemLayout<BLOCK_N, A_MN, B_MN>;
+  constexpr int kStages = L::kStages;
+  constexpr uint32_t kTmemCols = kAccumStages * BLOCK_N;      // 256 or 512: power of two >= 32
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* barrier_area = smem + kStages * L::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(barrier_area);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full_bar = empty_bar + kStages;
+  uint64_t* tmem_empty_bar = tmem_full_bar + kAccumStages;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + kAccumStages);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_m_blocks = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int num_n_blocks = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int num_tiles = num_m_blocks * num_n_blocks;
+  const int num_k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < kAccumStages; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], kNumEpilogueWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (one elected lane) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile % num_m_blocks) * BLOCK_M;
+        const int n0 = (tile / num_m_blocks) * BLOCK_N;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::kStageBytes;
+          uint8_t* sb = sa + L::kABytes;
+          mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+          const int k0 = kb * BLOCK_K;
+          if constexpr (!A_MN) {
+            tma_load_2d(&map_a, &full_bar[stage], sa, k0, m0);                    // box {64 k, 128 m}
+          } else {
+#pragma unroll
+            for (int c = 0; c < BLOCK_M / 64; ++c)                               // box {64 m, 64 k} per chunk
+              tma_load_2d(&map_a, &full_bar[stage], sa + c * (64 * BLOCK_K * 2), m0 + 64 * c, k0);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d(&map_b, &full_bar[stage], sb, k0, n0);                    // box {64 k, BLOCK_N n}
+          } else {
+#pragma unroll
+            for (int c = 0; c < BLOCK_N / 64; ++c)
+              tma_load_2d(&map_b, &full_bar[stage], sb + c * (64 * BLOCK_K * 2), n0 + 64 * c, k0);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one elected lane) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, A_MN, B_MN);
+      // K-major : SBO = 8 rows * 128 B, LBO unused ; advance 32 B per UMMA_K
+      // MN-major: SBO = 8 k-rows * 128 B, LBO = one 64-wide MN chunk (BLOCK_K rows * 128 B); advance 16 rows
+      constexpr uint32_t kSbo = 1024;
+      constexpr uint32_t kLboA = A_MN ? BLOCK_K * 128 : 16;
+      constexpr uint32_t kLboB = B_MN ? BLOCK_K * 128 : 16;
+      constexpr uint32_t kStepA = A_MN ? UMMA_K * 128 : UMMA_K * 2;
+      constexpr uint32_t kStepB = B_MN ? UMMA_K * 128 : UMMA_K * 2;
+      int stage = 0;
+      uint32_t phase = 0;
+      int accum = 0;
+      uint32_t accum_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty_bar[accum], accum_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(accum * BLOCK_N);
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * L::kStageBytes);
+          const uint32_t b_addr = a_addr + L::kABytes;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t da = make_smem_desc(a_addr + k * kStepA, kLboA, kSbo);
+            const uint64_t db = make_smem_desc(b_addr + k * kStepB, kLboB, kSbo);
+            umma_bf16(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);                       // smem slot reusable once these MMAs retire
+          if (kb == num_k_blocks - 1) umma_commit(&tmem_full_bar[accum]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        if (++accum == kAccumStages) { accum = 0; accum_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    const int ew = warp - 4;                         // == warp % 4: this warp may touch TMEM lanes [32*ew, 32*ew+32)
+    int accum = 0;
+    uint32_t accum_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile % num_m_blocks) * BLOCK_M;
+      const int n0 = (tile / num_m_blocks) * BLOCK_N;
+      mbar_wait(&tmem_full_bar[accum], accum_phase);
+      tc_fence_after();
+      const int row = m0 + ew * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(accum * BLOCK_N);
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr + (uint32_t)c, r);
+        tmem_ld_wait();
+        const int col0 = n0 + c;
+        if (row < p.M && col0 < p.N) {
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          if (p.epilogue >= 1 && p.bias != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i < p.N) v[i] += __bfloat162float(p.bias[col0 + i]);
+          }
+          if (p.epilogue == 2) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+          } else if (p.epilogue == 3) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+          }
+          const bool full = (col0 + 32 <= p.N);
+          if (p.out_fp32) {
+            float* out = reinterpret_cast<float*>(p.d) + (size_t)row * p.N + col0;
+            if (full && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                if (p.accumulate) { const float4 old = *reinterpret_cast<float4*>(out + i); o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+                *reinterpret_cast<float4*>(out + i) = o;
+              }
+            } else {
+              for (int i = 0; i < 32; ++i)
+                if (col0 + i < p.N) out[i] = p.accumulate ? out[i] + v[i] : v[i];
+            }
+          } else {
+            __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.d) + (size_t)row * p.N + col0;
+            if (full && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 8) {
+                __nv_bfloat162 h[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(v[i + 2 * q], v[i + 2 * q + 1]);
+                *reinterpret_cast<uint4*>(out + i) = *reinterpret_cast<uint4*>(h);
+              }
+            } else {
+              for (int i = 0; i < 32; ++i)
+                if (col0 + i < p.N) out[i] = __float2bfloat16_rn(v[i]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[accum]);     // this warp is done reading the accumulator
+      if (++accum == kAccumStages) { accum = 0; accum_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// ---------------- host side ------------------------------------------------------------------------
+struct MapKey {
+  const void* ptr; int rows, cols, box_rows, box_cols;
+  bool operator==(const MapKey& o) const { return ptr == o.ptr && rows == o.rows && cols == o.cols && box_rows == o.box_rows && box_cols == o.box_cols; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = std::hash<const void*>()(k.ptr);
+    for (int v : {k.rows, k.cols, k.box_rows, k.box_cols}) h = h * 1000003u ^ (size_t)v;
+    return h;
+  }
+};
+
+// 2-D row-major bf16 tensor [rows, cols]; box = [box_rows, box_cols] with box_cols * 2 == 128 bytes.
+CUtensorMap make_map(const void* ptr, int rows, int cols, int box_rows, int box_cols) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  MapKey key{ptr, rows, cols, box_rows, box_cols};
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+  }
+  auto& drv = Driver::get();
+  if (!drv.TensorMapEncodeTiled) throw std::runtime_error("gemm: cuTensorMapEncodeTiled unavailable");
+  CUtensorMap map;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t elem_strides[2] = {1, 1};
+  B200_DRV_CHECK(drv.TensorMapEncodeTiled(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box,
+                                          elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE));
+  std::lock_guard<std::mutex> g(mu);
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, map);
+  return map;
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN>
+void launch_variant(const void* a, const void* b, const GemmParams& p, cudaStream_t stream) {
+  using L = SmemLayout<BLOCK_N, A_MN, B_MN>;
+  // A: K-major stored [M,K] -> box {BLOCK_M rows, 64 cols};  MN-major stored [K,M] -> box {64 rows(k), 64 cols(m)}
+  CUtensorMap map_a = A_MN ? make_map(a, p.K, p.M, BLOCK_K, 64) : make_map(a, p.M, p.K, BLOCK_M, BLOCK_K);
+  CUtensorMap map_b = B_MN ? make_map(b, p.K, p.N, BLOCK_K, 64) : make_map(b, p.N, p.K, BLOCK_N, BLOCK_K);
+  auto kernel = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN>;
+  static bool configured = false;
+  if (!configured) {
+    B200_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    configured = true;
+  }
+  const int tiles = ceil_div(p.M, BLOCK_M) * ceil_div(p.N, BLOCK_N);
+  const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  kernel<<<grid, kNumThreads, L::kTotal, stream>>>(map_a, map_b, p);
+  B200_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace
+
+bool gemm_shape_supported(int M, int N, int K, bool a_mn, bool b_mn) {
+  if (M < 1 || N < 1 || K < 1) return false;
+  // TMA: global row pitch must be a multiple of 16 bytes
+  const int a_cols = a_mn ? M : K, b_cols = b_mn ? N : K;
+  if (a_cols % 8 != 0 || b_cols % 8 != 0) return false;
+  return true;
+}
+
+void launch_gemm_bf16(const void* a, const void* b, void* d, const void* bias, int M, int N, int K, bool a_mn, bool b_mn,
+                      int epilogue, DType out_dtype, bool accumulate, cudaStream_t stream) {
+  if (!gemm_shape_supported(M, N, K, a_mn, b_mn)) throw std::runtime_error("gemm_bf16: shape not TMA-compatible (row pitch % 16 B)");
+  if (out_dtype != DType::BF16 && out_dtype != DType::F32) throw std::runtime_error("gemm_bf16: output must be bf16 or fp32");
+  if (accumulate && out_dtype != DType::F32) throw std::runtime_error("gemm_bf16: accumulate needs fp32 output");
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.epilogue = epilogue;
+  p.out_fp32 = out_dtype == DType::F32 ? 1 : 0;
+  p.accumulate = accumulate ? 1 : 0;
+  p.d = d;
+  p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
+  const bool wide = N > 128;
+#define B200_GEMM_DISPATCH(AMN, BMN)                                                   \
+  if (a_mn == AMN && b_mn == BMN) {                                                    \
+    if (wide) launch_variant<256, AMN, BMN>(a, b, p, stream);                          \
+    else launch_variant<128, AMN, BMN>(a, b, p, stream);                               \
+    return;                                                                            \
+  }
+  B200_GEMM_DISPATCH(false, false)
+  B200_GEMM_DISPATCH(false, true)
+  B200_GEMM_DISPATCH(true, true)
+  B200_GEMM_DISPATCH(true, false)
+#undef B200_GEMM_DISPATCH
+}
+
+void launch_gemm_nt_bf16(const void* a, const void* b, void* d, const void* bias, int M, int N, int K, int epilogue,
+                         DType out_dtype, cudaStream_t stream) {
+  launch_gemm_bf16(a, b, d, bias, M, N, K, false, false, epilogue, out_dtype, false, stream);
+}
+
+}  // namespace b200
