@@ -275,7 +275,7 @@ void launch_bucket_allreduce(const CommCtx& ctx, const BucketTable& tab, size_t 
   else if (in_bf16) launch_typed<__nv_bfloat16, float>(args, algo, blocks, stream);
   else if (wire_bf16) launch_typed<float, __nv_bfloat16>(args, algo, blocks, stream);
   else launch_typed<float, float>(args, algo, blocks, stream);
-  B200_CUDA_CHECK(cudaGetLastError());
+  B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
 }
 
 }  // namespace b200

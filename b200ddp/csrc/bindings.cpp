@@ -187,6 +187,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.attr("ALGO_TWO_SHOT") = (int)kAlgoTwoShot;
   m.attr("ALGO_NVLS") = (int)kAlgoNvls;
 
+  m.def("launch_count", []() { return (long long)launch_counter().load(); });
   m.def("assign_by_size", &assign_by_size, py::arg("nbytes"), py::arg("keys"), py::arg("limits"), py::arg("max_tensors") = 0);
 
   py::class_<PeerArena>(m, "PeerArena")
@@ -233,15 +234,15 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def_readwrite("numels", &BucketPlan::numels)
       .def_readwrite("offsets", &BucketPlan::offsets)
       .def_readwrite("data_elems", &BucketPlan::data_elems)
-      .def_readwrite("total_elems", &BucketPlan::total_elems);
+      .def_readwrite("total_elems", &BucketPlan::total_elems)
+      .def_readwrite("grad_dtype", &BucketPlan::grad_dtype)
+      .def_readwrite("wire_dtype", &BucketPlan::wire_dtype);
 
   py::class_<Reducer>(m, "Reducer")
-      .def(py::init([](PeerArena& arena, std::vector<BucketPlan> plans, int num_params, int grad_dtype, int wire_dtype, int algo,
+      .def(py::init([](PeerArena& arena, std::vector<BucketPlan> plans, int num_params, int algo,
                        int max_blocks, long long one_shot_max_bytes, bool as_view, bool find_unused, double extra_scale,
                        double timeout_s) {
              ReducerOptions o;
-             o.grad_dtype = (DType)grad_dtype;
-             o.wire_dtype = (DType)wire_dtype;
              o.algo = algo;
              o.max_blocks = max_blocks;
              o.one_shot_max_bytes = one_shot_max_bytes;
@@ -390,6 +391,31 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     launch_gemm_nt_bf16(a.data_ptr(), b.data_ptr(), d.data_ptr(), bias_ptr, M, N, K, epilogue, dtype_of(d), cur_stream());
     return d;
   }, py::arg("a"), py::arg("b"), py::arg("bias") = py::none(), py::arg("epilogue") = 0, py::arg("out") = py::none());
+  // general form: a_mn=false -> a is [M,K]; true -> a is stored [K,M].  b_mn=false -> b is [N,K]; true -> stored [K,N].
+  m.def("gemm", [](at::Tensor a, at::Tensor b, c10::optional<at::Tensor> bias, bool a_mn, bool b_mn, int epilogue, bool out_fp32,
+                   c10::optional<at::Tensor> out) {
+    check_cuda(a, "a"); check_cuda(b, "b");
+    TORCH_CHECK(a.scalar_type() == at::kBFloat16 && b.scalar_type() == at::kBFloat16, "gemm: bf16 operands");
+    TORCH_CHECK(a.dim() == 2 && b.dim() == 2 && a.is_contiguous() && b.is_contiguous(), "gemm: 2-D contiguous operands");
+    c10::cuda::CUDAGuard guard(a.device());
+    const int M = (int)(a_mn ? a.size(1) : a.size(0)), K = (int)(a_mn ? a.size(0) : a.size(1));
+    const int N = (int)(b_mn ? b.size(1) : b.size(0)), Kb = (int)(b_mn ? b.size(0) : b.size(1));
+    TORCH_CHECK(K == Kb, "gemm: reduction dims differ (", K, " vs ", Kb, ")");
+    bool accumulate = false;
+    at::Tensor d;
+    if (out.has_value()) { d = *out; accumulate = d.scalar_type() == at::kFloat && out_fp32; }
+    else d = at::empty({M, N}, a.options().dtype(out_fp32 ? at::kFloat : at::kBFloat16));
+    TORCH_CHECK(d.is_contiguous() && d.size(0) == M && d.size(1) == N, "gemm: bad output");
+    const void* bias_ptr = nullptr;
+    if (bias.has_value()) {
+      TORCH_CHECK(bias->scalar_type() == at::kBFloat16 && bias->numel() == N, "gemm: bias bf16 [N]");
+      bias_ptr = bias->data_ptr();
+    }
+    launch_gemm_bf16(a.data_ptr(), b.data_ptr(), d.data_ptr(), bias_ptr, M, N, K, a_mn, b_mn, epilogue, dtype_of(d), accumulate,
+                     cur_stream());
+    return d;
+  }, py::arg("a"), py::arg("b"), py::arg("bias") = py::none(), py::arg("a_mn") = false, py::arg("b_mn") = false,
+     py::arg("epilogue") = 0, py::arg("out_fp32") = false, py::arg("out") = py::none());
   m.def("gemm_supported", &gemm_shape_supported);
 
   // ---- input pipeline ---------------------------------------------------------------------------

@@ -91,7 +91,7 @@ void launch_peer_broadcast(const CommCtx& ctx, const BucketTable& tab, size_t st
   args.use_mc = (use_multicast && ctx.mc_base != nullptr) ? 1 : 0;
   args.tab = tab;
   peer_broadcast_kernel<<<blocks, kCommThreads, 0, stream>>>(args);
-  B200_CUDA_CHECK(cudaGetLastError());
+  B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
 }
 
 // ---- link probes --------------------------------------------------------------------------------
@@ -120,15 +120,15 @@ __global__ void __launch_bounds__(kCommThreads) peer_barrier_kernel(const __grid
 
 void launch_peer_pull(const CommCtx& ctx, int peer, size_t src_off, void* dst, size_t bytes, int blocks, cudaStream_t stream) {
   peer_pull_kernel<<<blocks, kCommThreads, 0, stream>>>(ctx.base + (size_t)peer * ctx.stride + src_off, (char*)dst, bytes / 16);
-  B200_CUDA_CHECK(cudaGetLastError());
+  B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
 }
 void launch_peer_push(const CommCtx& ctx, int peer, size_t dst_off, const void* src, size_t bytes, int blocks, cudaStream_t stream) {
   peer_push_kernel<<<blocks, kCommThreads, 0, stream>>>((const char*)src, ctx.base + (size_t)peer * ctx.stride + dst_off, bytes / 16);
-  B200_CUDA_CHECK(cudaGetLastError());
+  B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
 }
 void launch_peer_barrier(const CommCtx& ctx, int blocks, cudaStream_t stream) {
   peer_barrier_kernel<<<blocks, kCommThreads, 0, stream>>>(ctx);
-  B200_CUDA_CHECK(cudaGetLastError());
+  B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
 }
 
 }  // namespace b200

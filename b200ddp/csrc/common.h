@@ -17,7 +17,16 @@
     }                                                                                              \
   } while (0)
 
+#include <atomic>
+
 namespace b200 {
+
+// every kernel launch issued by this extension is counted (bench.py reports it as gpu_launches)
+inline std::atomic<long long>& launch_counter() {
+  static std::atomic<long long> c{0};
+  return c;
+}
+#define B200_COUNT_LAUNCH(n) ::b200::launch_counter().fetch_add((n), std::memory_order_relaxed)
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74
 constexpr int kWarp = 32;

@@ -378,7 +378,7 @@ void launch_variant(const void* a, const void* b, const GemmParams& p, cudaStrea
   const int tiles = ceil_div(p.M, BLOCK_M) * ceil_div(p.N, BLOCK_N);
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
   kernel<<<grid, kNumThreads, L::kTotal, stream>>>(map_a, map_b, p);
-  B200_CUDA_CHECK(cudaGetLastError());
+  B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
 }
 
 }  // namespace

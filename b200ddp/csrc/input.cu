@@ -38,7 +38,7 @@ void launch_normalize_to_channels_last(const void* src, DType src_dt, void* dst,
   else if (su8) normalize_cl_kernel<unsigned char, float><<<blocks, 256, 0, s>>>((const unsigned char*)src, (float*)dst, n, c, h, w, mean, inv_std, in_scale);
   else if (dbf) normalize_cl_kernel<float, __nv_bfloat16><<<blocks, 256, 0, s>>>((const float*)src, (__nv_bfloat16*)dst, n, c, h, w, mean, inv_std, in_scale);
   else normalize_cl_kernel<float, float><<<blocks, 256, 0, s>>>((const float*)src, (float*)dst, n, c, h, w, mean, inv_std, in_scale);
-  B200_CUDA_CHECK(cudaGetLastError());
+  B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
 }
 
 }  // namespace b200

@@ -71,7 +71,7 @@ void launch_small_linear_fwd(const float* x, const float* w, const float* b, flo
   int blocks = (M * N + kSmallThreads - 1) / kSmallThreads;
   if (blocks > kNumSMs) blocks = kNumSMs;
   small_linear_fwd_kernel<<<blocks, kSmallThreads, smem, s>>>(x, w, b, y, M, N, K, relu);
-  B200_CUDA_CHECK(cudaGetLastError());
+  B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
 }
 
 void launch_small_linear_bwd(const float* dy, const float* x, const float* w, const float* y, float* dx, float* dw, float* db, int M, int N,
@@ -79,7 +79,7 @@ void launch_small_linear_bwd(const float* dy, const float* x, const float* w, co
   const size_t smem = (size_t)M * N * sizeof(float);
   if (smem > 48 * 1024) throw std::runtime_error("small_linear_bwd: activation gradient does not fit the small-shape kernel");
   small_linear_bwd_kernel<<<1, kSmallThreads, smem, s>>>(dy, x, w, y, dx, dw, db, M, N, K, relu, accumulate);
-  B200_CUDA_CHECK(cudaGetLastError());
+  B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
 }
 
 }  // namespace b200

@@ -114,7 +114,7 @@ void launch_mse_fwd_bwd(const void* out, const void* target, DType dt, size_t n,
   else
     mse_fwd_bwd_kernel<float><<<blocks, kLossThreads, 0, s>>>((const float*)out, (const float*)target, n, gscale, loss,
                                                              (float*)dout, scratch);
-  B200_CUDA_CHECK(cudaGetLastError());
+  B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
 }
 
 void launch_xent_fwd_bwd(const void* logits, const long long* targets, DType dt, int rows, int cols, long long ignore_index,
@@ -129,9 +129,9 @@ void launch_xent_fwd_bwd(const void* logits, const long long* targets, DType dt,
   else
     xent_fwd_bwd_kernel<float><<<rows, kLossThreads, 0, s>>>((const float*)logits, targets, rows, cols, ignore_index, g, row_loss,
                                                            (float*)dlogits);
-  B200_CUDA_CHECK(cudaGetLastError());
+  B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
   xent_finish_kernel<<<1, 1024, 0, s>>>(row_loss, targets, rows, cols, ignore_index, loss);
-  B200_CUDA_CHECK(cudaGetLastError());
+  B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
 }
 
 }  // namespace b200

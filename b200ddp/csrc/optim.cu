@@ -103,13 +103,13 @@ void launch_multi_sqnorm(const OptTable& tab, DType g_dtype, float* partials, cu
   if (tab.total_blocks <= 0) return;
   if (g_dtype == DType::BF16) multi_sqnorm_kernel<__nv_bfloat16><<<tab.total_blocks, kOptThreads, 0, s>>>(tab, partials);
   else multi_sqnorm_kernel<float><<<tab.total_blocks, kOptThreads, 0, s>>>(tab, partials);
-  B200_CUDA_CHECK(cudaGetLastError());
+  B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
 }
 
 void launch_clip_coef(const float* partials, int n, float max_norm, float grad_scale, float* coef_out, float* norm_out,
                       cudaStream_t s) {
   clip_coef_kernel<<<1, 1024, 0, s>>>(partials, n, max_norm, grad_scale, coef_out, norm_out);
-  B200_CUDA_CHECK(cudaGetLastError());
+  B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
 }
 
 void launch_multi_sgd(const OptTable& tab, DType p_dtype, DType g_dtype, const SgdHyper& h, cudaStream_t s) {
@@ -119,7 +119,7 @@ void launch_multi_sgd(const OptTable& tab, DType p_dtype, DType g_dtype, const S
   else if (pb) multi_sgd_kernel<__nv_bfloat16, float><<<tab.total_blocks, kOptThreads, 0, s>>>(tab, h);
   else if (gb) multi_sgd_kernel<float, __nv_bfloat16><<<tab.total_blocks, kOptThreads, 0, s>>>(tab, h);
   else multi_sgd_kernel<float, float><<<tab.total_blocks, kOptThreads, 0, s>>>(tab, h);
-  B200_CUDA_CHECK(cudaGetLastError());
+  B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
 }
 
 void launch_scale_inplace(float* x, size_t n, const float* scalar, cudaStream_t s) {
@@ -127,7 +127,7 @@ void launch_scale_inplace(float* x, size_t n, const float* scalar, cudaStream_t 
   if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
   if (blocks < 1) blocks = 1;
   scale_inplace_kernel<<<blocks, 256, 0, s>>>(x, n, scalar);
-  B200_CUDA_CHECK(cudaGetLastError());
+  B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
 }
 
 }  // namespace b200

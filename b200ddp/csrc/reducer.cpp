@@ -54,7 +54,6 @@ Reducer::Reducer(PeerArena* arena, std::vector<BucketPlan> plans, int num_params
   where_.assign(num_params, {-1, -1});
   fired_.assign(num_params, 0);
   buckets_.resize(plans_.size());
-  const size_t wire_size = dtype_size(opt_.wire_dtype);
   for (size_t b = 0; b < plans_.size(); ++b) {
     const BucketPlan& p = plans_[b];
     BucketState& s = buckets_[b];
@@ -71,7 +70,7 @@ Reducer::Reducer(PeerArena* arena, std::vector<BucketPlan> plans, int num_params
       s.table.t[k].off = p.offsets[k];
       where_.at(p.param_indices[k]) = {(int)b, k};
     }
-    const size_t wire_bytes = (size_t)p.total_elems * wire_size;
+    const size_t wire_bytes = (size_t)p.total_elems * dtype_size((DType)p.wire_dtype);
     s.stage_off = arena_->alloc(wire_bytes, 4096);
     // algorithm + grid per bucket (static, so every rank picks the same)
     int algo = opt_.algo;
@@ -143,12 +142,12 @@ void Reducer::launch_bucket(int b, cudaStream_t compute) {
   float* sq = sq_partials_ ? sq_partials_ + (size_t)b * sq_stride_ : nullptr;
   const float scale = opt_.extra_scale / (float)ctx_.world;
   const bool scatter = !opt_.as_view;
-  launch_bucket_allreduce(ctx_, s.table, s.stage_off, opt_.grad_dtype, opt_.wire_dtype, s.algo, s.blocks,
+  launch_bucket_allreduce(ctx_, s.table, s.stage_off, (DType)plans_[b].grad_dtype, (DType)plans_[b].wire_dtype, s.algo, s.blocks,
                           (opt_.as_view || opt_.find_unused) ? s.flat_out : nullptr, sq,
                           opt_.find_unused ? s.flags_dev : nullptr, scale, scatter, comm_stream_);
   s.launched = true;
   ++launches;
-  bytes_on_wire += (long long)s.table.total_elems * (long long)dtype_size(opt_.wire_dtype);
+  bytes_on_wire += (long long)s.table.total_elems * (long long)dtype_size((DType)plans_[b].wire_dtype);
 }
 
 int Reducer::finalize(uintptr_t compute_stream) {

@@ -33,11 +33,11 @@ struct BucketPlan {
   std::vector<uint32_t> offsets;
   uint32_t data_elems = 0;
   uint32_t total_elems = 0;
+  int grad_dtype = 0;   // DType of this bucket's gradients (buckets are planned per dtype)
+  int wire_dtype = 0;   // DType on the wire
 };
 
 struct ReducerOptions {
-  DType grad_dtype = DType::F32;
-  DType wire_dtype = DType::BF16;
   int algo = kAlgoAuto;
   int max_blocks = 32;
   long long one_shot_max_bytes = 256 * 1024;

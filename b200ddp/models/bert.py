@@ -1,0 +1,117 @@
+"""BERT-base encoder + MLM head for the "BERT-base DDP bf16, seq 512" config in BASELINE.json.
+Every linear is a ``b200ddp.ops.Linear`` (tcgen05 GEMM with bias / bias+GELU epilogues), every
+LayerNorm the hand-written kernel, the loss the fused cross-entropy; attention uses torch's SDPA
+(library flash attention - not a named hot op).  109.5 M encoder parameters as in SURVEY §2.4-K4
+(199 tensors) when built with ``with_mlm_head=False``."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ..ops import LayerNorm, Linear
+
+
+@dataclass
+class BertConfig:
+    vocab_size: int = 30522
+    hidden: int = 768
+    layers: int = 12
+    heads: int = 12
+    intermediate: int = 3072
+    max_position: int = 512
+    type_vocab: int = 2
+    eps: float = 1e-12
+    dropout: float = 0.0
+
+
+class BertEmbeddings(nn.Module):
+    def __init__(self, c: BertConfig):
+        super().__init__()
+        self.word_embeddings = nn.Embedding(c.vocab_size, c.hidden)
+        self.position_embeddings = nn.Embedding(c.max_position, c.hidden)
+        self.token_type_embeddings = nn.Embedding(c.type_vocab, c.hidden)
+        self.LayerNorm = LayerNorm(c.hidden, eps=c.eps)
+        self.dropout = nn.Dropout(c.dropout)
+
+    def forward(self, input_ids, token_type_ids=None):
+        B, S = input_ids.shape
+        pos = torch.arange(S, device=input_ids.device)
+        if token_type_ids is None:
+            token_type_ids = torch.zeros_like(input_ids)
+        x = self.word_embeddings(input_ids) + self.position_embeddings(pos)[None] + self.token_type_embeddings(token_type_ids)
+        return self.dropout(self.LayerNorm(x))
+
+
+class BertLayer(nn.Module):
+    def __init__(self, c: BertConfig):
+        super().__init__()
+        self.heads = c.heads
+        self.query = Linear(c.hidden, c.hidden)
+        self.key = Linear(c.hidden, c.hidden)
+        self.value = Linear(c.hidden, c.hidden)
+        self.attn_out = Linear(c.hidden, c.hidden)
+        self.attn_norm = LayerNorm(c.hidden, eps=c.eps)
+        self.ffn_in = Linear(c.hidden, c.intermediate, activation="gelu")
+        self.ffn_out = Linear(c.intermediate, c.hidden)
+        self.ffn_norm = LayerNorm(c.hidden, eps=c.eps)
+        self.dropout = nn.Dropout(c.dropout)
+
+    def forward(self, x, attn_mask=None):
+        B, S, H = x.shape
+        hd = H // self.heads
+
+        def split(t):
+            return t.view(B, S, self.heads, hd).transpose(1, 2)
+
+        q, k, v = split(self.query(x)), split(self.key(x)), split(self.value(x))
+        a = F.scaled_dot_product_attention(q, k, v, attn_mask=attn_mask)
+        a = a.transpose(1, 2).reshape(B, S, H)
+        x = self.attn_norm(x + self.dropout(self.attn_out(a)))
+        return self.ffn_norm(x + self.dropout(self.ffn_out(self.ffn_in(x))))
+
+
+class BertModel(nn.Module):
+    def __init__(self, config: BertConfig | None = None, with_pooler: bool = True):
+        super().__init__()
+        c = self.config = config or BertConfig()
+        self.embeddings = BertEmbeddings(c)
+        self.encoder = nn.ModuleList([BertLayer(c) for _ in range(c.layers)])
+        self.pooler = Linear(c.hidden, c.hidden) if with_pooler else None
+        self.apply(self._init)
+
+    @staticmethod
+    def _init(m):
+        if isinstance(m, (Linear, nn.Embedding)):
+            nn.init.normal_(m.weight, std=0.02)
+            if getattr(m, "bias", None) is not None:
+                nn.init.zeros_(m.bias)
+
+    def forward(self, input_ids, token_type_ids=None, attn_mask=None):
+        x = self.embeddings(input_ids, token_type_ids)
+        for layer in self.encoder:
+            x = layer(x, attn_mask)
+        return x
+
+
+class BertForMaskedLM(nn.Module):
+    """Encoder + tied-embedding MLM head; forward returns logits [B, S, vocab]."""
+
+    def __init__(self, config: BertConfig | None = None):
+        super().__init__()
+        self.bert = BertModel(config, with_pooler=False)
+        c = self.bert.config
+        self.transform = Linear(c.hidden, c.hidden, activation="gelu")
+        self.transform_norm = LayerNorm(c.hidden, eps=c.eps)
+        self.decoder_bias = nn.Parameter(torch.zeros(c.vocab_size))
+
+    def forward(self, input_ids, token_type_ids=None, attn_mask=None):
+        from ..ops import linear
+        h = self.transform_norm(self.transform(self.bert(input_ids, token_type_ids, attn_mask)))
+        return linear(h, self.bert.embeddings.word_embeddings.weight, self.decoder_bias)
+
+
+def bert_base(with_mlm_head: bool = True) -> nn.Module:
+    return BertForMaskedLM() if with_mlm_head else BertModel()

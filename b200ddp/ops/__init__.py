@@ -1,0 +1,4 @@
+from .functional import linear, mse_loss, cross_entropy, layer_norm
+from .modules import Linear, LayerNorm, MSELoss, CrossEntropyLoss
+
+__all__ = ["linear", "mse_loss", "cross_entropy", "layer_norm", "Linear", "LayerNorm", "MSELoss", "CrossEntropyLoss"]

@@ -179,7 +179,8 @@ class DistributedDataParallel(nn.Module):
         self.backend_name = pick_backend_name(backend, device)
         if self.backend_name == "b200":
             from .peer import PeerCollectives
-            self.comm = PeerCollectives.get(process_group, device)
+            grad_bytes = sum(p.numel() * max(4, p.element_size()) for p in self._params)
+            self.comm = PeerCollectives.get(process_group, device, min_bytes=int(grad_bytes * 1.25))
         else:
             self.comm = TorchCollectives(process_group)
         self.world_size = self.comm.world
@@ -201,8 +202,9 @@ class DistributedDataParallel(nn.Module):
                                       find_unused_parameters)
         self._callback_queued = False
         self._hook_handles = []
-        for i, p in enumerate(self._params):
-            self._hook_handles.append(p.register_post_accumulate_grad_hook(self._make_hook(i)))
+        if self.world_size > 1:   # a single rank has nothing to reduce: no hooks, zero overhead
+            for i, p in enumerate(self._params):
+                self._hook_handles.append(p.register_post_accumulate_grad_hook(self._make_hook(i)))
 
     # ---- wrap-time checks / broadcast -------------------------------------------------------
     def _verify_params_across_ranks(self) -> None:
@@ -245,7 +247,7 @@ class DistributedDataParallel(nn.Module):
         self.reducer.finalize()
 
     def forward(self, *inputs, **kwargs):
-        if self.require_backward_grad_sync and torch.is_grad_enabled():
+        if self.world_size > 1 and self.require_backward_grad_sync and torch.is_grad_enabled():
             self.reducer.reset()
             self._sync_buffers()
         return self.module(*inputs, **kwargs)

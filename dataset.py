@@ -1,0 +1,2 @@
+"""User-replaceable data, as in the reference layout (synthetic, seeded identically on every rank)."""
+from b200ddp.data import FooDataset, SyntheticImageNet, SyntheticTokens  # noqa: F401

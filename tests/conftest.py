@@ -1,0 +1,34 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "multigpu: needs >= 2 CUDA devices")
+
+
+def pytest_collection_modifyitems(config, items):
+    import torch
+    have = torch.cuda.is_available()
+    ngpu = torch.cuda.device_count() if have else 0
+    for item in items:
+        if "gpu" in item.keywords and not have:
+            item.add_marker(pytest.mark.skip(reason="no CUDA device"))
+        if "multigpu" in item.keywords and ngpu < 2:
+            item.add_marker(pytest.mark.skip(reason="needs >= 2 GPUs"))
+
+
+@pytest.fixture()
+def free_port():
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port

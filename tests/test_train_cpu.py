@@ -1,0 +1,100 @@
+"""End-to-end CPU runs of the template: CLI, checkpoint layout, resume, accumulation, gloo launcher."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from b200ddp.engine import cli
+from b200ddp.engine.trainer import Trainer
+from b200ddp.models import FooModel
+from b200ddp.ops import MSELoss, cross_entropy, layer_norm, linear, mse_loss
+from b200ddp.optim import FusedSGD
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(tmp_path, *flags):
+    args = cli.build_parser().parse_args(["--no_cuda", "--no_tensorboard", "--output_dir", str(tmp_path / "out"),
+                                          "--dataset_size", "640", *flags])
+    cli.setup(args)
+    trainer = Trainer(args, FooModel(), cli.log)
+    return trainer, trainer.train()
+
+
+def test_single_process_run_checkpoint_layout(tmp_path):
+    trainer, (global_step, avg_loss) = _run(tmp_path, "--max_steps", "30", "--logging_steps", "10", "--save_steps", "20")
+    assert global_step == 31                              # starts at 1, exits when > max_steps (reference ddp.py:206,280)
+    assert 0.5 < avg_loss < 2.0
+    ckpt = tmp_path / "out" / "checkpoint-20"
+    assert sorted(os.listdir(ckpt)) == ["model.bin", "optimizer.pt", "scheduler.pt", "trainer_state.pt", "training_args.bin"]
+    state = torch.load(ckpt / "model.bin")
+    assert list(state.keys()) == ["net1.weight", "net1.bias", "net2.weight", "net2.bias"]
+    assert tuple(state["net2.weight"].shape) == (5, 10)
+    saved_args = torch.load(ckpt / "training_args.bin", weights_only=False)
+    assert saved_args.max_steps == 30 and saved_args.per_gpu_train_batch_size == 32
+    assert not (tmp_path / "out" / "checkpoint-40").exists()
+
+
+def test_accumulation_saves_once_per_boundary(tmp_path):
+    trainer, (global_step, _) = _run(tmp_path, "--max_steps", "6", "--gradient_accumulation_steps", "4", "--save_steps", "2",
+                                     "--logging_steps", "2")
+    assert global_step == 7
+    assert sorted(os.listdir(tmp_path / "out")) == ["checkpoint-2", "checkpoint-4", "checkpoint-6"]
+    assert trainer.step_fn.micro_steps == 6 * 4
+
+
+def test_resume_restores_state(tmp_path):
+    t1, _ = _run(tmp_path, "--max_steps", "10", "--save_steps", "10", "--seed", "3")
+    w_after_10 = torch.load(tmp_path / "out" / "checkpoint-10" / "model.bin")["net1.weight"]
+    t2, (gs, _) = _run(tmp_path, "--max_steps", "14", "--save_steps", "0", "--seed", "3", "--resume_from", "latest")
+    assert t2._resume_state["global_step"] == 10 and gs == 15
+    assert t2.scheduler.last_step == 9 + 5                # 9 steps before the save + 5 after resume
+    assert not torch.equal(t2.model.net1.weight.detach(), w_after_10)   # training continued from the restored weights
+
+
+def test_evaluate_returns_loss(tmp_path):
+    trainer, _ = _run(tmp_path, "--max_steps", "5", "--save_steps", "0")
+    res = trainer.evaluate(max_batches=3)
+    assert res["eval_samples"] == 96 and res["eval_loss"] > 0
+
+
+def test_fused_sgd_cpu_matches_torch_sgd_with_clip():
+    torch.manual_seed(0)
+    a, b = FooModel(), FooModel()
+    b.load_state_dict(a.state_dict())
+    oa = FusedSGD(a.parameters(), lr=0.1, momentum=0.9, weight_decay=1e-2, nesterov=True, max_grad_norm=0.05)
+    ob = torch.optim.SGD(b.parameters(), lr=0.1, momentum=0.9, weight_decay=1e-2, nesterov=True)
+    for i in range(5):
+        x, y = torch.randn(16, 10), torch.randn(16, 5)
+        for m, o in ((a, oa), (b, ob)):
+            o.zero_grad()
+            torch.nn.functional.mse_loss(m(x), y).backward()
+        torch.nn.utils.clip_grad_norm_(b.parameters(), 0.05)
+        oa.step(); ob.step()
+    for pa, pb in zip(a.parameters(), b.parameters()):
+        assert torch.allclose(pa, pb, atol=1e-6)
+
+
+def test_cpu_ops_match_torch():
+    torch.manual_seed(0)
+    x, w, b = torch.randn(7, 12), torch.randn(5, 12), torch.randn(5)
+    assert torch.allclose(linear(x, w, b, "relu"), torch.relu(torch.nn.functional.linear(x, w, b)))
+    assert torch.allclose(mse_loss(x, x * 0.5), torch.nn.functional.mse_loss(x, x * 0.5))
+    t = torch.randint(0, 12, (7,))
+    assert torch.allclose(cross_entropy(x, t), torch.nn.functional.cross_entropy(x, t))
+    g, be = torch.randn(12), torch.randn(12)
+    assert torch.allclose(layer_norm(x, g, be), torch.nn.functional.layer_norm(x, (12,), g, be))
+
+
+def test_torchrun_gloo_two_ranks(tmp_path, free_port):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(free_port), os.path.join(ROOT, "ddp.py"), "--no_cuda", "--no_tensorboard", "--max_steps", "12",
+           "--save_steps", "6", "--logging_steps", "6", "--dataset_size", "512", "--output_dir", str(tmp_path / "o")]
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env, cwd=str(tmp_path))
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "[Finished training.] [global_step=13]" in res.stdout
+    assert sorted(os.listdir(tmp_path / "o")) == ["checkpoint-12", "checkpoint-6"]
+    assert "backend='gloo'" in res.stdout and "world_size=2" in res.stdout
