@@ -26,7 +26,7 @@ from ..data import BatchLoader, DevicePrefetcher, FooDataset, SyntheticImageNet,
 from ..ops import CrossEntropyLoss, MSELoss
 from ..optim import FusedSGD, get_linear_schedule_with_warmup
 from ..parallel import DataParallel, DistributedDataParallel, ShardedSampler
-from ..utils import is_main_process, rng_state, restore_rng_state
+from ..utils import is_main_process, rng_state, restore_rng_state, to_mixed_bf16
 from ..utils.checkpoint import latest_checkpoint, load_checkpoint, save_checkpoint
 from .step import TrainStep
 
@@ -83,7 +83,7 @@ class Trainer:
             self.compute_dtype = torch.bfloat16
         model = model.to(self.device)
         if self.compute_dtype != torch.float32:
-            model = model.to(self.compute_dtype)
+            model = to_mixed_bf16(model)
         if getattr(args, "channels_last", False):
             model = model.to(memory_format=torch.channels_last)
 
@@ -108,17 +108,13 @@ class Trainer:
         else:
             self.t_total = steps_per_epoch * args.num_train_epochs
 
-        # ---- loss / optimizer / schedule ------------------------------------------------------------
+        # ---- resume (weights first: rank 0's reach every rank through the wrap-time broadcast) -----
         self.criterion = criterion if criterion is not None else build_criterion(args)
-        self.optimizer = FusedSGD(model.parameters(), lr=getattr(args, "lr", 1e-3), momentum=getattr(args, "momentum", 0.0),
-                                  weight_decay=getattr(args, "weight_decay", 0.0), max_grad_norm=args.max_grad_norm)
-        self.scheduler = get_linear_schedule_with_warmup(self.optimizer, num_warmup_steps=args.warmup_steps,
-                                                         num_training_steps=self.t_total)
         if self.resume_dir:
-            self._resume_state = load_checkpoint(self.resume_dir, model, self.optimizer, self.scheduler)
-            log.info("Resumed from checkpoint.", dict(path=self.resume_dir, global_step=self._resume_state.get("global_step")))
+            load_checkpoint(self.resume_dir, model)
 
         # ---- parallel wrapper ---------------------------------------------------------------------
+        inner = model
         if args.n_gpu > 1:
             model = DataParallel(model)
         elif self.distributed:
@@ -129,6 +125,15 @@ class Trainer:
                 gradient_as_bucket_view=getattr(args, "gradient_as_bucket_view", False),
                 bucket_cap_mb=getattr(args, "bucket_cap_mb", None), backend=getattr(args, "backend", "auto"),
                 wire_dtype=getattr(args, "wire_dtype", None), broadcast_buffers=getattr(args, "broadcast_buffers", True))
+
+        # ---- optimizer / schedule: built AFTER the broadcast so fp32 master weights start identical --
+        self.optimizer = FusedSGD(inner.parameters(), lr=getattr(args, "lr", 1e-3), momentum=getattr(args, "momentum", 0.0),
+                                  weight_decay=getattr(args, "weight_decay", 0.0), max_grad_norm=args.max_grad_norm)
+        self.scheduler = get_linear_schedule_with_warmup(self.optimizer, num_warmup_steps=args.warmup_steps,
+                                                         num_training_steps=self.t_total)
+        if self.resume_dir:
+            self._resume_state = load_checkpoint(self.resume_dir, None, self.optimizer, self.scheduler)
+            log.info("Resumed from checkpoint.", dict(path=self.resume_dir, global_step=self._resume_state.get("global_step")))
         self.model = model
         self.step_fn = TrainStep(model, self.criterion, self.optimizer, self.device,
                                  accumulation=args.gradient_accumulation_steps, use_graph=getattr(args, "cuda_graph", False),

@@ -12,6 +12,7 @@ BERT config named in BASELINE.json.
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional
 
 import torch
@@ -115,7 +116,8 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     if x.is_cuda:
         N, K = weight.shape
         M = x.numel() // K
-        if x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and _tc_ok(M, N, K) and (bias is not None or activation is None):
+        if x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and _tc_ok(M, N, K) \
+                and (bias is not None or activation is None) and os.environ.get("B200DDP_DISABLE_TC", "0") != "1":
             return _LinearTC.apply(x, weight, bias, activation)
         if x.dtype == torch.float32 and weight.dtype == torch.float32 and N * (K + 1) * 4 <= 48 * 1024 and M * N * 4 <= 48 * 1024 \
                 and activation in (None, "relu"):

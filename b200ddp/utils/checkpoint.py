@@ -82,8 +82,9 @@ def latest_checkpoint(output_dir: str) -> Optional[str]:
 def load_checkpoint(ckpt_dir: str, model, optimizer=None, scheduler=None, map_location="cpu") -> dict:
     """Restore what exists in ``ckpt_dir``; returns the trainer state dict ({} for reference-made
     checkpoints, which carry none)."""
-    state = torch.load(os.path.join(ckpt_dir, MODEL_FILE), map_location=map_location, weights_only=True)
-    unwrap(model).load_state_dict(state)
+    if model is not None:
+        state = torch.load(os.path.join(ckpt_dir, MODEL_FILE), map_location=map_location, weights_only=True)
+        unwrap(model).load_state_dict(state)
     opt_path = os.path.join(ckpt_dir, OPTIMIZER_FILE)
     if optimizer is not None and os.path.isfile(opt_path):
         optimizer.load_state_dict(torch.load(opt_path, map_location=map_location, weights_only=False))

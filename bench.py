@@ -171,6 +171,7 @@ def run_ours(args):
     from b200ddp.ops import CrossEntropyLoss, MSELoss
     from b200ddp.optim import FusedSGD, get_linear_schedule_with_warmup
     from b200ddp.parallel import DistributedDataParallel, ShardedSampler
+    from b200ddp.utils import to_mixed_bf16
 
     rank, local_rank, world = dist_env()
     assert world == args.gpus, f"WORLD_SIZE={world} but --gpus {args.gpus}: launch with torchrun --nproc-per-node {args.gpus}"
@@ -185,12 +186,11 @@ def run_ours(args):
     is_image = args.model.startswith("resnet")
     model = build_model(args.model).to(dev)
     if args.model != "foo":
-        model = model.to(torch.bfloat16)
+        model = to_mixed_bf16(model)
     if is_image:
         model = model.to(memory_format=torch.channels_last)
     compute_dtype = torch.float32 if args.model == "foo" else torch.bfloat16
-    opt = FusedSGD(model.parameters(), lr=1e-3, max_grad_norm=1000.0)
-    sched = get_linear_schedule_with_warmup(opt, num_warmup_steps=100, num_training_steps=100000)
+    inner = model
     backend = args.backend
     if world > 1:
         model = DistributedDataParallel(model, device_ids=[local_rank], find_unused_parameters=False,
@@ -199,6 +199,8 @@ def run_ours(args):
         backend = model.backend_name
     else:
         backend = "single"
+    opt = FusedSGD(inner.parameters(), lr=1e-3, max_grad_norm=1000.0)     # after the wrap-time broadcast
+    sched = get_linear_schedule_with_warmup(opt, num_warmup_steps=100, num_training_steps=100000)
     criterion = CrossEntropyLoss() if args.model.startswith("bert") else MSELoss()
 
     # input pipeline kernel: raw fp32 NCHW batch -> bf16 channels_last, straight into the graph's input buffer
