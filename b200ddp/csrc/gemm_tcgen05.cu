@@ -349,6 +349,9 @@ CUtensorMap make_map(const void* ptr, int rows, int cols, int box_rows, int box_
   }
   auto& drv = Driver::get();
   if (!drv.TensorMapEncodeTiled) throw std::runtime_error("gemm: cuTensorMapEncodeTiled unavailable");
+  // driver-API calls need a current context; autograd worker threads only get one lazily from the runtime
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) { B200_CUDA_CHECK(cudaFree(nullptr)); ctx_bound = true; }
   CUtensorMap map;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)cols * 2};

@@ -20,6 +20,7 @@ from typing import Dict, Iterable, List, Optional
 import torch
 
 from .. import _ext
+from ..utils.precision import is_dense
 
 _DTYPE_CODE = {torch.float32: 0, torch.bfloat16: 1}
 
@@ -72,7 +73,7 @@ class FusedSGD(torch.optim.Optimizer):
         for dtype, ps in by_dtype.items():
             # keep parameter storage dense: the kernel walks physical order
             for p in ps:
-                if not (p.is_contiguous() or p.is_non_overlapping_and_dense()):
+                if not is_dense(p):
                     p.data = p.data.contiguous()
             g = _NativeGroup(C, ps, base)
             base = g.flat_end

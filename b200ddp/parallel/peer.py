@@ -16,6 +16,7 @@ import torch
 import torch.distributed as dist
 
 from .. import _ext
+from ..utils.precision import is_dense
 from .buckets import BucketSpec
 
 MiB = 1 << 20
@@ -132,7 +133,7 @@ class PeerCollectives:
         dense = []
         fixups = []
         for t in tensors:
-            if t.is_contiguous() or t.is_non_overlapping_and_dense():
+            if is_dense(t):
                 dense.append(t)
             else:
                 c = t.contiguous()
@@ -222,7 +223,7 @@ class NativeReducer:
     def mark_ready(self, index: int) -> None:
         p = self.params[index]
         g = p.grad
-        if not g.is_contiguous() and not g.is_non_overlapping_and_dense():
+        if not is_dense(g):
             g = g.contiguous()
             p.grad = g
         self._last_fired.add(index)

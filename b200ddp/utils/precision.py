@@ -17,3 +17,18 @@ def to_mixed_bf16(model: nn.Module, keep_norm_fp32: bool = True) -> nn.Module:
             if isinstance(m, _KEEP_FP32):
                 m.float()
     return model
+
+
+def is_dense(t: torch.Tensor) -> bool:
+    """True when the tensor's elements occupy one gap-free block of storage (any permutation of strides)."""
+    if t.is_contiguous():
+        return True
+    try:
+        from torch._prims_common import is_non_overlapping_and_dense
+        return bool(is_non_overlapping_and_dense(t))
+    except Exception:
+        if t.dim() == 4:
+            return t.is_contiguous(memory_format=torch.channels_last)
+        if t.dim() == 5:
+            return t.is_contiguous(memory_format=torch.channels_last_3d)
+        return False
