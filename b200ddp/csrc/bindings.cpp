@@ -202,6 +202,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def("has_multicast", &PeerArena::has_multicast)
       .def("alloc", &PeerArena::alloc, py::arg("nbytes"), py::arg("align") = 256)
       .def("used", &PeerArena::used)
+      .def("rewind", &PeerArena::rewind)
       .def("bytes", &PeerArena::bytes)
       .def("rank", &PeerArena::rank)
       .def("world", &PeerArena::world)

@@ -80,6 +80,157 @@ __global__ void __launch_bounds__(kLnThreads) layernorm_bwd_kernel(const T* __re
   }
 }
 
+
+// ---- fast path: cols % 8 == 0 and cols <= 1024 (BERT hidden 768/1024) ----------------------------------
+// A lane owns up to 4 chunks of 8 consecutive columns (chunk c covers columns [8*(lane+32c), +8)): one
+// 16-byte load per chunk, the row lives in registers, statistics need no second pass over memory.
+constexpr int kLnChunks = 4;
+
+template <typename T> __device__ __forceinline__ void ln_load8(const T* p, float* f);
+template <> __device__ __forceinline__ void ln_load8<float>(const float* p, float* f) {
+  const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+template <> __device__ __forceinline__ void ln_load8<__nv_bfloat16>(const __nv_bfloat16* p, float* f) {
+  unpack8(*reinterpret_cast<const Bf16x8*>(p), f);
+}
+template <typename T> __device__ __forceinline__ void ln_store8(T* p, const float* f);
+template <> __device__ __forceinline__ void ln_store8<float>(float* p, const float* f) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
+}
+template <> __device__ __forceinline__ void ln_store8<__nv_bfloat16>(__nv_bfloat16* p, const float* f) {
+  *reinterpret_cast<Bf16x8*>(p) = pack8(f);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kLnThreads) layernorm_fwd_fast_kernel(const T* __restrict__ x, const T* __restrict__ gamma,
+                                                                        const T* __restrict__ beta, int rows, int cols, float eps,
+                                                                        T* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd) {
+  const int lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+  const int nchunk = cols >> 3;
+  float g[kLnChunks][8], b[kLnChunks][8];
+#pragma unroll
+  for (int c = 0; c < kLnChunks; ++c) {
+    const int ch = lane + 32 * c;
+    if (ch < nchunk) { ln_load8<T>(gamma + 8 * ch, g[c]); ln_load8<T>(beta + 8 * ch, b[c]); }
+  }
+  const float inv = 1.f / (float)cols;
+  for (int row = blockIdx.x * warps + (threadIdx.x >> 5); row < rows; row += gridDim.x * warps) {
+    const T* xr = x + (size_t)row * cols;
+    float v[kLnChunks][8];
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < kLnChunks; ++c) {
+      const int ch = lane + 32 * c;
+      if (ch < nchunk) {
+        ln_load8<T>(xr + 8 * ch, v[c]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += v[c][j];
+      }
+    }
+    const float mu = warp_sum(s) * inv;
+    float q = 0.f;
+#pragma unroll
+    for (int c = 0; c < kLnChunks; ++c) {
+      if (lane + 32 * c < nchunk) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float d = v[c][j] - mu; q += d * d; }
+      }
+    }
+    const float rs = rsqrtf(warp_sum(q) * inv + eps);
+    T* yr = y + (size_t)row * cols;
+#pragma unroll
+    for (int c = 0; c < kLnChunks; ++c) {
+      const int ch = lane + 32 * c;
+      if (ch < nchunk) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (v[c][j] - mu) * rs * g[c][j] + b[c][j];
+        ln_store8<T>(yr + 8 * ch, o);
+      }
+    }
+    if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kLnThreads) layernorm_bwd_fast_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ gamma,
+                                                                        const float* __restrict__ mean, const float* __restrict__ rstd, int rows,
+                                                                        int cols, T* __restrict__ dx, float* __restrict__ dgamma_partial,
+                                                                        float* __restrict__ dbeta_partial) {
+  extern __shared__ float smem[];            // [2][cols] per-CTA column accumulators
+  float* sg = smem;
+  float* sb = smem + cols;
+  for (int i = threadIdx.x; i < 2 * cols; i += blockDim.x) smem[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  const int nchunk = cols >> 3;
+  float g[kLnChunks][8], ag[kLnChunks][8], ab[kLnChunks][8];
+#pragma unroll
+  for (int c = 0; c < kLnChunks; ++c) {
+    const int ch = lane + 32 * c;
+    if (ch < nchunk) ln_load8<T>(gamma + 8 * ch, g[c]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { ag[c][j] = 0.f; ab[c][j] = 0.f; }
+  }
+  const float inv = 1.f / (float)cols;
+  const int rows_per_cta = (rows + gridDim.x - 1) / gridDim.x;
+  const int r0 = blockIdx.x * rows_per_cta;
+  const int r1 = min(rows, r0 + rows_per_cta);
+  for (int row = r0 + warp; row < r1; row += warps) {
+    const T* xr = x + (size_t)row * cols;
+    const T* dyr = dy + (size_t)row * cols;
+    const float mu = mean[row], rs = rstd[row];
+    float xn[kLnChunks][8], d[kLnChunks][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < kLnChunks; ++c) {
+      const int ch = lane + 32 * c;
+      if (ch < nchunk) {
+        ln_load8<T>(xr + 8 * ch, xn[c]);
+        ln_load8<T>(dyr + 8 * ch, d[c]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          xn[c][j] = (xn[c][j] - mu) * rs;
+          const float dg = d[c][j] * g[c][j];
+          s1 += dg;
+          s2 += dg * xn[c][j];
+          ag[c][j] += d[c][j] * xn[c][j];
+          ab[c][j] += d[c][j];
+        }
+      }
+    }
+    s1 = warp_sum(s1) * inv;
+    s2 = warp_sum(s2) * inv;
+    T* dxr = dx + (size_t)row * cols;
+#pragma unroll
+    for (int c = 0; c < kLnChunks; ++c) {
+      const int ch = lane + 32 * c;
+      if (ch < nchunk) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = rs * (d[c][j] * g[c][j] - s1 - xn[c][j] * s2);
+        ln_store8<T>(dxr + 8 * ch, o);
+      }
+    }
+  }
+  // one shared-memory reduction per warp per column at the very end
+#pragma unroll
+  for (int c = 0; c < kLnChunks; ++c) {
+    const int ch = lane + 32 * c;
+    if (ch < nchunk) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { atomicAdd(&sg[8 * ch + j], ag[c][j]); atomicAdd(&sb[8 * ch + j], ab[c][j]); }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < cols; i += blockDim.x) {
+    dgamma_partial[(size_t)blockIdx.x * cols + i] = sg[i];
+    dbeta_partial[(size_t)blockIdx.x * cols + i] = sb[i];
+  }
+}
+
 template <typename T>
 __global__ void layernorm_bwd_finish_kernel(const float* __restrict__ dgamma_partial, const float* __restrict__ dbeta_partial, int parts,
                                             int cols, T* __restrict__ dgamma, T* __restrict__ dbeta) {
@@ -105,7 +256,16 @@ void launch_layernorm_fwd(const void* x, const void* gamma, const void* beta, DT
   int blocks = (rows + 7) / 8;
   if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
   if (blocks < 1) blocks = 1;
-  if (dt == DType::BF16)
+  const bool fast = (cols % 8 == 0) && cols <= 8 * 32 * kLnChunks &&
+                    ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(gamma) |
+                      reinterpret_cast<uintptr_t>(beta)) & 31u) == 0;
+  if (fast && dt == DType::BF16)
+    layernorm_fwd_fast_kernel<__nv_bfloat16><<<blocks, kLnThreads, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)gamma,
+                                                                         (const __nv_bfloat16*)beta, rows, cols, eps, (__nv_bfloat16*)y, mean, rstd);
+  else if (fast)
+    layernorm_fwd_fast_kernel<float><<<blocks, kLnThreads, 0, s>>>((const float*)x, (const float*)gamma, (const float*)beta, rows, cols, eps,
+                                                                 (float*)y, mean, rstd);
+  else if (dt == DType::BF16)
     layernorm_fwd_kernel<__nv_bfloat16><<<blocks, kLnThreads, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)gamma,
                                                                     (const __nv_bfloat16*)beta, rows, cols, eps, (__nv_bfloat16*)y, mean, rstd);
   else
@@ -118,7 +278,21 @@ void launch_layernorm_bwd(const void* dy, const void* x, const void* gamma, cons
                           int cols, void* dx, float* dgamma_partial, float* dbeta_partial, int partial_rows, void* dgamma,
                           void* dbeta, cudaStream_t s) {
   const size_t smem = 2 * (size_t)cols * sizeof(float);
-  if (dt == DType::BF16) {
+  const bool fast = (cols % 8 == 0) && cols <= 8 * 32 * kLnChunks &&
+                    ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx) |
+                      reinterpret_cast<uintptr_t>(gamma)) & 31u) == 0;
+  if (fast && dt == DType::BF16) {
+    layernorm_bwd_fast_kernel<__nv_bfloat16><<<partial_rows, kLnThreads, smem, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,
+                                                                                  (const __nv_bfloat16*)gamma, mean, rstd, rows, cols,
+                                                                                  (__nv_bfloat16*)dx, dgamma_partial, dbeta_partial);
+    layernorm_bwd_finish_kernel<__nv_bfloat16><<<(cols + 255) / 256, 256, 0, s>>>(dgamma_partial, dbeta_partial, partial_rows, cols,
+                                                                                (__nv_bfloat16*)dgamma, (__nv_bfloat16*)dbeta);
+  } else if (fast) {
+    layernorm_bwd_fast_kernel<float><<<partial_rows, kLnThreads, smem, s>>>((const float*)dy, (const float*)x, (const float*)gamma, mean, rstd,
+                                                                          rows, cols, (float*)dx, dgamma_partial, dbeta_partial);
+    layernorm_bwd_finish_kernel<float><<<(cols + 255) / 256, 256, 0, s>>>(dgamma_partial, dbeta_partial, partial_rows, cols,
+                                                                        (float*)dgamma, (float*)dbeta);
+  } else if (dt == DType::BF16) {
     layernorm_bwd_kernel<__nv_bfloat16><<<partial_rows, kLnThreads, smem, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,
                                                                              (const __nv_bfloat16*)gamma, mean, rstd, rows, cols,
                                                                              (__nv_bfloat16*)dx, dgamma_partial, dbeta_partial);

@@ -54,6 +54,7 @@ class PeerArena {
   // symmetric bump allocation (same call sequence on every rank -> same offsets)
   size_t alloc(size_t nbytes, size_t align = 256);
   size_t used() const { return bump_; }
+  void rewind(size_t mark) { if (mark >= kSignalBytes && mark <= bump_) bump_ = mark; }   // release everything allocated after `mark`
 
   // device-visible error word (pinned, mapped): kernels write a code on barrier timeout
   volatile int* error_word_host() const { return err_host_; }

@@ -286,9 +286,11 @@ class DistributedDataParallel(nn.Module):
         keys = [(str(p.dtype), str(p.device)) for p in self._params]
         self._specs = plan_buckets([p.numel() for p in self._params], [p.element_size() for p in self._params],
                                    keys, self.bucket_cap_bytes, self.first_bucket_bytes, ready_order=order)
-        self.reducer = type(self.reducer).rebuilt(self.reducer, self._specs) if hasattr(type(self.reducer), "rebuilt") \
-            else _PyReducer(self._params, self._specs, self.comm, self.gradient_as_bucket_view,
-                            self.find_unused_parameters)
+        if hasattr(self.reducer, "rebuilt"):
+            self.reducer = self.reducer.rebuilt(self._specs)
+        else:
+            self.reducer = _PyReducer(self._params, self._specs, self.comm, self.gradient_as_bucket_view,
+                                      self.find_unused_parameters)
         return True
 
     def state_dict(self, *args, **kwargs):

@@ -194,6 +194,8 @@ class NativeReducer:
             plan.wire_dtype = _DTYPE_CODE[wire]
             plans.append(plan)
         blocks = max_blocks or comm.blocks
+        self._arena_mark = comm.arena.used()
+        self._ctor = dict(wire_dtype=wire_dtype, algo=algo, max_blocks=max_blocks)
         one_shot_max = int(os.environ.get("B200DDP_ONE_SHOT_MAX_KB", "256")) * 1024
         self._c = C.Reducer(comm.arena, plans, len(params), _ALGO[algo], blocks, one_shot_max, gradient_as_bucket_view,
                             find_unused, 1.0, comm.timeout_s)
@@ -256,6 +258,15 @@ class NativeReducer:
                     flags = self._c.read_used_flags(b)
                 if flags[k] > 0.0:   # used on some other rank: take the reduced value from the flat bucket
                     p.grad = self.views[b][k] if self.as_view else self.views[b][k].clone()
+
+    def rebuilt(self, specs: List[BucketSpec]) -> "NativeReducer":
+        """New reducer for a new bucket plan; the old staging regions go back to the arena first."""
+        self._c.synchronize()
+        torch.cuda.synchronize(self.params[0].device)
+        self.comm.barrier()
+        del self._c
+        self.comm.arena.rewind(self._arena_mark)
+        return NativeReducer(self.params, specs, self.comm, self.as_view, self.find_unused, **self._ctor)
 
     @property
     def stats(self) -> dict:

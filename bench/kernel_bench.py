@@ -1,0 +1,184 @@
+#!/usr/bin/env python
+"""Per-kernel timings against the measured roofline (MEASURED_PEAKS.json: HBM copy GB/s, cuBLAS bf16 TFLOP/s).
+
+  python bench/kernel_bench.py [--only gemm,sgd,ln,xent,mse,input] [--out gpurun_out/kernels.json] [--iters 20]
+
+Timing hygiene (B200_PROFILING.md): >= 3 warm-up launches, CUDA events on the launching stream, a 256 MB write
+between timed launches to flush the 126 MB L2, median of `iters`.  Each entry reports algorithmic bytes / FLOPs,
+achieved rate and the fraction of the measured peak; cuBLAS / torch timings of the same op are printed beside
+ours as the library baseline.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        d = json.load(open(path))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+_flush = None
+
+
+def timeit(fn, iters=20, flush=True):
+    global _flush
+    if _flush is None:
+        _flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(iters):
+        if flush:
+            _flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    return statistics.median(times)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", type=str, default="gemm,sgd,ln,xent,mse,input")
+    ap.add_argument("--out", type=str, default=None)
+    ap.add_argument("--iters", type=int, default=20)
+    args = ap.parse_args()
+    from b200ddp import _ext
+    from b200ddp.ops import functional as Fn
+    from b200ddp.optim import FusedSGD
+    C = _ext.get()
+    hbm, tf_burst, tf_sust, src = peaks()
+    dev = torch.device("cuda", 0)
+    want = set(args.only.split(","))
+    rows = []
+
+    def record(name, ms, flops=None, bytes_=None, lib_ms=None, note=""):
+        row = {"kernel": name, "ms": ms, "lib_ms": lib_ms, "note": note}
+        if flops:
+            row["tflops"] = flops / ms / 1e9
+            row["frac_of_peak"] = row["tflops"] / tf_burst
+            row["peak"] = f"{tf_burst} TFLOP/s cuBLAS bf16 burst ({src})"
+        if bytes_:
+            row["gbs"] = bytes_ / ms / 1e6
+            row["frac_of_peak"] = row["gbs"] / hbm
+            row["peak"] = f"{hbm} GB/s copy ({src})"
+        rows.append(row)
+        lib = f" | lib {lib_ms:8.3f} ms ({ms / lib_ms:4.2f}x lib time)" if lib_ms else ""
+        rate = f"{row.get('tflops', 0):8.1f} TFLOP/s" if flops else f"{row.get('gbs', 0):8.1f} GB/s"
+        print(f"{name:44s} {ms:8.3f} ms {rate} {100 * row.get('frac_of_peak', 0):5.1f}% of peak{lib} {note}", flush=True)
+
+    if "gemm" in want:
+        shapes = [(8192, 8192, 8192), (16384, 768, 768), (16384, 3072, 768), (16384, 768, 3072), (16384, 2304, 768),
+                  (4096, 30528, 768), (32, 1000, 2048)]
+        for M, N, K in shapes:
+            a = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
+            b = torch.randn(N, K, device=dev, dtype=torch.bfloat16)
+            out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+            ms = timeit(lambda: C.gemm(a, b, None, False, False, 0, False, out), args.iters)
+            lib = timeit(lambda: torch.matmul(a, b.t(), out=out), args.iters)
+            record(f"gemm_nt {M}x{N}x{K}", ms, flops=2.0 * M * N * K, lib_ms=lib)
+        # backward layouts on the BERT FFN shape
+        M, N, K = 16384, 3072, 768
+        dy = torch.randn(M, N, device=dev, dtype=torch.bfloat16)
+        w = torch.randn(N, K, device=dev, dtype=torch.bfloat16)
+        x = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
+        ms = timeit(lambda: C.gemm(dy, w, None, False, True, 0, False, None), args.iters)
+        lib = timeit(lambda: torch.matmul(dy, w), args.iters)
+        record(f"gemm dgrad {M}x{K}x{N}", ms, flops=2.0 * M * N * K, lib_ms=lib)
+        ms = timeit(lambda: C.gemm(dy, x, None, True, True, 0, False, None), args.iters)
+        lib = timeit(lambda: torch.matmul(dy.t(), x), args.iters)
+        record(f"gemm wgrad {N}x{K}x{M}", ms, flops=2.0 * M * N * K, lib_ms=lib)
+        bias = torch.randn(N, device=dev, dtype=torch.bfloat16)
+        ms = timeit(lambda: C.gemm(x, w, bias, False, False, 3, False, None), args.iters)
+        lib = timeit(lambda: torch.nn.functional.gelu(torch.nn.functional.linear(x, w, bias)), args.iters)
+        record(f"gemm+bias+gelu {M}x{N}x{K}", ms, flops=2.0 * M * N * K, lib_ms=lib, note="lib = cuBLAS linear + gelu kernel")
+
+    if "sgd" in want:
+        for dtype, label in ((torch.float32, "fp32"), (torch.bfloat16, "bf16+master")):
+            import torchvision
+            shapes = [tuple(p.shape) for p in torchvision.models.resnet50().parameters()]
+            params = [torch.nn.Parameter(torch.randn(*s, device=dev).to(dtype)) for s in shapes]
+            n = sum(p.numel() for p in params)
+            for p in params:
+                p.grad = torch.randn_like(p)
+            opt = FusedSGD(params, lr=1e-3, max_grad_norm=1000.0)
+            ms = timeit(lambda: opt.step(), args.iters)
+            es = 4 if dtype == torch.float32 else 2
+            # norm pass reads g; update reads g + master/param, writes master (+ param)
+            byt = n * (es + es + (4 + 4 if dtype == torch.float32 else 4 + 4 + 2))
+            ref = [torch.nn.Parameter(p.detach().float().clone()) for p in params]
+            for r, p in zip(ref, params):
+                r.grad = p.grad.float()
+            ropt = torch.optim.SGD(ref, lr=1e-3)
+
+            def lib_step():
+                torch.nn.utils.clip_grad_norm_(ref, 1000.0)
+                ropt.step()
+            lib = timeit(lib_step, args.iters)
+            record(f"clip+sgd resnet50 161 tensors {label}", ms, bytes_=byt, lib_ms=lib, note="lib = clip_grad_norm_ + foreach SGD (fp32)")
+
+    if "ln" in want:
+        rows_, cols = 16384, 768
+        x = torch.randn(rows_, cols, device=dev, dtype=torch.bfloat16, requires_grad=True)
+        g = torch.randn(cols, device=dev, dtype=torch.bfloat16)
+        b = torch.randn(cols, device=dev, dtype=torch.bfloat16)
+        ms = timeit(lambda: C.layernorm_fwd(x, g, b, 1e-5), args.iters)
+        lib = timeit(lambda: torch.nn.functional.layer_norm(x, (cols,), g, b), args.iters)
+        record(f"layernorm fwd {rows_}x{cols} bf16", ms, bytes_=rows_ * cols * 2 * 2, lib_ms=lib)
+        y, mean, rstd = C.layernorm_fwd(x, g, b, 1e-5)
+        dy = torch.randn_like(y)
+        ms = timeit(lambda: C.layernorm_bwd(dy, x, g, mean, rstd), args.iters)
+        yl = torch.nn.functional.layer_norm(x, (cols,), g.clone().requires_grad_(), b.clone().requires_grad_())
+        lib = timeit(lambda: torch.autograd.grad(yl, x, dy, retain_graph=True), args.iters)
+        record(f"layernorm bwd {rows_}x{cols} bf16", ms, bytes_=rows_ * cols * 2 * 3, lib_ms=lib, note="lib computes dx only")
+
+    if "xent" in want:
+        rows_, cols = 4096, 30522
+        x = torch.randn(rows_, cols, device=dev, dtype=torch.bfloat16)
+        t = torch.randint(0, cols, (rows_,), device=dev)
+        ms = timeit(lambda: C.xent_fwd_bwd(x, t, -100, 1.0), args.iters)
+        xr = x.clone().requires_grad_()
+
+        def lib_xent():
+            loss = torch.nn.functional.cross_entropy(xr.float(), t)
+            torch.autograd.grad(loss, xr)
+        lib = timeit(lib_xent, args.iters)
+        record(f"xent fwd+bwd {rows_}x{cols} bf16", ms, bytes_=rows_ * cols * 2 * 2, lib_ms=lib, note="min traffic = read logits + write dlogits")
+
+    if "mse" in want:
+        n = 64 * 1024 * 1024
+        o = torch.randn(n, device=dev, dtype=torch.bfloat16)
+        t = torch.randn(n, device=dev, dtype=torch.bfloat16)
+        ms = timeit(lambda: C.mse_fwd_bwd(o, t, 1.0), args.iters)
+        record(f"mse fwd+bwd {n} bf16", ms, bytes_=n * 2 * 3)
+
+    if "input" in want:
+        x = torch.randn(256, 3, 224, 224, device=dev)
+        dst = torch.empty(x.shape, device=dev, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        mean, istd = torch.zeros(3, device=dev), torch.ones(3, device=dev)
+        ms = timeit(lambda: C.normalize_to_channels_last(x, dst, mean, istd, 1.0), args.iters)
+        lib = timeit(lambda: x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last), args.iters)
+        record("normalize+cast+NHWC 256x3x224x224", ms, bytes_=x.numel() * 6, lib_ms=lib)
+
+    if args.out:
+        os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
+        json.dump({"peaks": {"hbm_gbs": hbm, "bf16_tflops_burst": tf_burst, "bf16_tflops_sustained": tf_sust, "source": src},
+                   "rows": rows}, open(args.out, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
