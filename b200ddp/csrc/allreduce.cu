@@ -28,7 +28,7 @@ struct ArArgs {
 
 template <typename InT, int VE>
 __device__ __forceinline__ void gather_vec(const TensorSlot* slots, const uint32_t* offs, int count,
-                                           uint32_t data_elems, uint32_t e0, float scale, float* f) {
+                                           uint32_t data_elems, uint32_t e0, float scale, float* f, int& hint) {
   if (e0 >= data_elems) {  // "used" flags ride behind the data
 #pragma unroll
     for (int i = 0; i < VE; ++i) {
@@ -37,7 +37,9 @@ __device__ __forceinline__ void gather_vec(const TensorSlot* slots, const uint32
     }
     return;
   }
-  const int k = find_slot(offs, count, e0);
+  int k = hint;
+  if (!(offs[k] <= e0 && e0 < offs[k + 1])) k = find_slot(offs, count, e0);
+  hint = k;
   const uint32_t idx = e0 - offs[k];
   const uint32_t n = slots[k].numel;
   const InT* src = reinterpret_cast<const InT*>(slots[k].ptr);
@@ -75,7 +77,7 @@ __device__ __forceinline__ void gather_vec(const TensorSlot* slots, const uint32
 
 template <typename InT, int VE>
 __device__ __forceinline__ float deliver_vec(const ArArgs& a, const TensorSlot* slots, const uint32_t* offs,
-                                             uint32_t e0, const float* f) {
+                                             uint32_t e0, const float* f, int& hint) {
   const int count = a.tab.count;
   if (e0 >= a.tab.data_elems) {
     if (a.flags_out != nullptr) {
@@ -105,7 +107,9 @@ __device__ __forceinline__ float deliver_vec(const ArArgs& a, const TensorSlot* 
     }
   }
   if (a.scatter) {
-    const int k = find_slot(offs, count, e0);
+    int k = hint;
+    if (!(offs[k] <= e0 && e0 < offs[k + 1])) k = find_slot(offs, count, e0);
+    hint = k;
     const uint32_t idx = e0 - offs[k];
     const uint32_t n = slots[k].numel;
     InT* dst = reinterpret_cast<InT*>(slots[k].ptr);
@@ -153,87 +157,118 @@ __global__ void __launch_bounds__(kCommThreads, 1) bucket_allreduce_kernel(const
   const uint32_t first = blockIdx.x * blockDim.x + threadIdx.x;
   char* const my_stage = c.base + (size_t)r * c.stride + a.stage_off;
   float sq = 0.f;
+  int hint = 0;
+  constexpr int U = 4;    // independent 16-byte requests in flight per thread and loop trip
 
   // ---- phase 1: gather + scale + cast into local symmetric staging
   for (int s = 0; s < P; ++s) {
-    for (uint32_t j = first; j < Vs; j += step) {
-      const uint32_t v = (uint32_t)s * Vs + j;
-      if (v >= V) break;
-      float f[VE];
-      gather_vec<InT, VE>(slots, offs, count, a.tab.data_elems, v * VE, a.scale, f);
-      *reinterpret_cast<Vec16*>(my_stage + (size_t)v * 16) = W::pack(f);
+    const uint32_t base_v = (uint32_t)s * Vs;
+    const uint32_t lim = min(Vs, V > base_v ? V - base_v : 0u);     // vectors of this slice that exist
+    for (uint32_t j = first; j < lim; j += U * step) {
+      float f[U][VE];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint32_t jj = j + u * step;
+        if (jj < lim) gather_vec<InT, VE>(slots, offs, count, a.tab.data_elems, (base_v + jj) * VE, a.scale, f[u], hint);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint32_t jj = j + u * step;
+        if (jj < lim) *reinterpret_cast<Vec16*>(my_stage + (size_t)(base_v + jj) * 16) = W::pack(f[u]);
+      }
     }
   }
   peer_block_barrier(c);
 
   if constexpr (ALGO == kAlgoOneShot) {
     // ---- every rank pulls every vector from every peer and reduces locally
-    for (int s = 0; s < P; ++s) {
-      for (uint32_t j = first; j < Vs; j += step) {
-        const uint32_t v = (uint32_t)s * Vs + j;
-        if (v >= V) break;
-        Vec16 x[kMaxRanks];
+    hint = 0;
+    for (uint32_t v = first; v < V; v += step) {
+      Vec16 x[kMaxRanks];
 #pragma unroll
-        for (int p = 0; p < kMaxRanks; ++p)
-          if (p < P) x[p] = ld_sys(c.base + (size_t)p * c.stride + a.stage_off + (size_t)v * 16);
-        float acc[VE];
+      for (int p = 0; p < kMaxRanks; ++p)
+        if (p < P) x[p] = ld_sys(c.base + (size_t)p * c.stride + a.stage_off + (size_t)v * 16);
+      float acc[VE];
 #pragma unroll
-        for (int i = 0; i < VE; ++i) acc[i] = 0.f;
+      for (int i = 0; i < VE; ++i) acc[i] = 0.f;
 #pragma unroll
-        for (int p = 0; p < kMaxRanks; ++p)
-          if (p < P) {
-            float f[VE];
-            W::unpack(x[p], f);
+      for (int p = 0; p < kMaxRanks; ++p)
+        if (p < P) {
+          float f[VE];
+          W::unpack(x[p], f);
 #pragma unroll
-            for (int i = 0; i < VE; ++i) acc[i] += f[i];
-          }
-        // round through the wire format so every algorithm yields the same values
-        Vec16 packed = W::pack(acc);
-        W::unpack(packed, acc);
-        sq += deliver_vec<InT, VE>(a, slots, offs, v * VE, acc);
-      }
+          for (int i = 0; i < VE; ++i) acc[i] += f[i];
+        }
+      // round through the wire format so every algorithm yields the same values
+      Vec16 packed = W::pack(acc);
+      W::unpack(packed, acc);
+      sq += deliver_vec<InT, VE>(a, slots, offs, v * VE, acc, hint);
     }
     peer_block_barrier(c);   // nobody may repack its staging while a peer still reads it
   } else {
     // ---- phase 2: reduce-scatter my slice, then all-gather it to every peer
-    for (uint32_t j = first; j < Vs; j += step) {
-      const uint32_t v = (uint32_t)r * Vs + j;
-      if (v >= V) break;
-      const size_t byte_off = a.stage_off + (size_t)v * 16;
-      if constexpr (ALGO == kAlgoNvls) {
-        Vec16 red16 = W::mc_reduce(c.mc_base + byte_off);
-        multimem_st(c.mc_base + byte_off, red16);
-      } else {
-        Vec16 x[kMaxRanks];
+    const uint32_t base_v = (uint32_t)r * Vs;
+    const uint32_t lim = min(Vs, V > base_v ? V - base_v : 0u);
+    if constexpr (ALGO == kAlgoNvls) {
+      for (uint32_t j = first; j < lim; j += U * step) {
+        Vec16 red16[U];
 #pragma unroll
-        for (int p = 0; p < kMaxRanks; ++p)
-          if (p < P) x[p] = ld_sys(c.base + (size_t)p * c.stride + byte_off);
-        float acc[VE];
+        for (int u = 0; u < U; ++u)
+          if (j + u * step < lim) red16[u] = W::mc_reduce(c.mc_base + a.stage_off + (size_t)(base_v + j + u * step) * 16);
 #pragma unroll
-        for (int i = 0; i < VE; ++i) acc[i] = 0.f;
+        for (int u = 0; u < U; ++u)
+          if (j + u * step < lim) multimem_st(c.mc_base + a.stage_off + (size_t)(base_v + j + u * step) * 16, red16[u]);
+      }
+    } else {
+      constexpr int U2 = 2;
+      for (uint32_t j = first; j < lim; j += U2 * step) {
+        Vec16 x[U2][kMaxRanks];
 #pragma unroll
-        for (int p = 0; p < kMaxRanks; ++p)
-          if (p < P) {
-            float f[VE];
-            W::unpack(x[p], f);
+        for (int u = 0; u < U2; ++u)
 #pragma unroll
-            for (int i = 0; i < VE; ++i) acc[i] += f[i];
-          }
-        const Vec16 out = W::pack(acc);
+          for (int p = 0; p < kMaxRanks; ++p)
+            if (p < P && j + u * step < lim)
+              x[u][p] = ld_sys(c.base + (size_t)p * c.stride + a.stage_off + (size_t)(base_v + j + u * step) * 16);
 #pragma unroll
-        for (int p = 0; p < kMaxRanks; ++p)
-          if (p < P) st_sys(c.base + (size_t)p * c.stride + byte_off, out);
+        for (int u = 0; u < U2; ++u) {
+          if (j + u * step >= lim) continue;
+          float acc[VE];
+#pragma unroll
+          for (int i = 0; i < VE; ++i) acc[i] = 0.f;
+#pragma unroll
+          for (int p = 0; p < kMaxRanks; ++p)
+            if (p < P) {
+              float f[VE];
+              W::unpack(x[u][p], f);
+#pragma unroll
+              for (int i = 0; i < VE; ++i) acc[i] += f[i];
+            }
+          const Vec16 out = W::pack(acc);
+          const size_t byte_off = a.stage_off + (size_t)(base_v + j + u * step) * 16;
+#pragma unroll
+          for (int p = 0; p < kMaxRanks; ++p)
+            if (p < P) st_sys(c.base + (size_t)p * c.stride + byte_off, out);
+        }
       }
     }
     peer_block_barrier(c);
     // ---- phase 3: cast back + scatter from local staging
+    hint = 0;
     for (int s = 0; s < P; ++s) {
-      for (uint32_t j = first; j < Vs; j += step) {
-        const uint32_t v = (uint32_t)s * Vs + j;
-        if (v >= V) break;
-        float f[VE];
-        W::unpack(ld_cg(my_stage + (size_t)v * 16), f);
-        sq += deliver_vec<InT, VE>(a, slots, offs, v * VE, f);
+      const uint32_t bv = (uint32_t)s * Vs;
+      const uint32_t ls = min(Vs, V > bv ? V - bv : 0u);
+      for (uint32_t j = first; j < ls; j += U * step) {
+        Vec16 x[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (j + u * step < ls) x[u] = ld_cg(my_stage + (size_t)(bv + j + u * step) * 16);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (j + u * step >= ls) continue;
+          float f[VE];
+          W::unpack(x[u], f);
+          sq += deliver_vec<InT, VE>(a, slots, offs, (bv + j + u * step) * VE, f, hint);
+        }
       }
     }
   }

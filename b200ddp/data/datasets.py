@@ -26,6 +26,11 @@ class FooDataset(Dataset):
         """Whole-batch gather (one index_select instead of B ``__getitem__`` calls + collate)."""
         return self.X.index_select(0, indices), self.Y.index_select(0, indices)
 
+    def batch_into(self, indices: torch.Tensor, outs) -> None:
+        """Gather straight into caller-owned (pinned) buffers: one pass over the data."""
+        torch.index_select(self.X, 0, indices, out=outs[0])
+        torch.index_select(self.Y, 0, indices, out=outs[1])
+
 
 class SyntheticImageNet(Dataset):
     """ImageNet-shaped samples: image fp32 (or uint8) [3,224,224]; target either a dense fp32
@@ -57,6 +62,11 @@ class SyntheticImageNet(Dataset):
     def batch(self, indices: torch.Tensor):
         return self.X.index_select(0, indices), self.Y.index_select(0, indices)
 
+    def batch_into(self, indices: torch.Tensor, outs) -> None:
+        """Gather straight into caller-owned (pinned) buffers: one pass over the data."""
+        torch.index_select(self.X, 0, indices, out=outs[0])
+        torch.index_select(self.Y, 0, indices, out=outs[1])
+
 
 class SyntheticTokens(Dataset):
     """Token ids [seq] + MLM labels [seq] (-100 = not predicted) for the BERT config."""
@@ -77,3 +87,8 @@ class SyntheticTokens(Dataset):
 
     def batch(self, indices: torch.Tensor):
         return self.X.index_select(0, indices), self.Y.index_select(0, indices)
+
+    def batch_into(self, indices: torch.Tensor, outs) -> None:
+        """Gather straight into caller-owned (pinned) buffers: one pass over the data."""
+        torch.index_select(self.X, 0, indices, out=outs[0])
+        torch.index_select(self.Y, 0, indices, out=outs[1])

@@ -13,14 +13,21 @@ Here:
 """
 from __future__ import annotations
 
+import queue
+import threading
 from typing import Iterator, List, Optional, Sequence, Tuple
 
 import torch
 
 
+class PinnedBatch(tuple):
+    """A batch living in one of the loader's pinned slots; ``slot`` lets the prefetcher mark it busy."""
+    slot: int = -1
+
+
 class BatchLoader:
     def __init__(self, dataset, batch_size: int, sampler=None, drop_last: bool = False, pin_memory: bool = True,
-                 num_slots: int = 4):
+                 num_slots: int = 6, background: bool = True):
         self.dataset = dataset
         self.batch_size = int(batch_size)
         self.sampler = sampler if sampler is not None else torch.utils.data.SequentialSampler(dataset)
@@ -29,6 +36,10 @@ class BatchLoader:
         self.num_slots = num_slots
         self._slots: List[Optional[Tuple[torch.Tensor, ...]]] = [None] * num_slots
         self._fast = hasattr(dataset, "batch")
+        self._into = hasattr(dataset, "batch_into")
+        # gather batches on a helper thread (index_select / memcpy release the GIL) so the training thread only
+        # ever launches work; depth is bounded by the number of pinned slots
+        self.background = bool(background) and self.pin
         # set by DevicePrefetcher: event that fires when the async H2D copy out of a pinned slot is done
         self.slot_events: List[Optional["torch.cuda.Event"]] = [None] * num_slots
         self.last_slot = 0
@@ -45,6 +56,42 @@ class BatchLoader:
         return cur
 
     def __iter__(self) -> Iterator[Tuple[torch.Tensor, ...]]:
+        if not self.background:
+            yield from self._produce()
+            return
+        q: "queue.Queue" = queue.Queue(maxsize=max(1, self.num_slots - 3))
+        stop = threading.Event()
+        END = object()
+
+        def work():
+            try:
+                for item in self._produce():
+                    while not stop.is_set():
+                        try:
+                            q.put(item, timeout=0.1)
+                            break
+                        except queue.Full:
+                            continue
+                    if stop.is_set():
+                        return
+                q.put(END)
+            except BaseException as exc:   # surface loader errors in the consumer
+                q.put(exc)
+
+        t = threading.Thread(target=work, name="b200ddp-batch-loader", daemon=True)
+        t.start()
+        try:
+            while True:
+                item = q.get()
+                if item is END:
+                    break
+                if isinstance(item, BaseException):
+                    raise item
+                yield item
+        finally:
+            stop.set()
+
+    def _produce(self) -> Iterator[Tuple[torch.Tensor, ...]]:
         indices: List[int] = []
         slot = 0
         for idx in self.sampler:
@@ -56,6 +103,11 @@ class BatchLoader:
         if indices and not self.drop_last:
             yield self._make(indices, slot)
 
+    def _tag(self, fields, slot: int):
+        b = PinnedBatch(fields)
+        b.slot = slot
+        return b
+
     def _make(self, indices: List[int], slot: int) -> Tuple[torch.Tensor, ...]:
         self.last_slot = slot
         busy = self.slot_events[slot]
@@ -66,11 +118,15 @@ class BatchLoader:
             idx = torch.as_tensor(indices, dtype=torch.long)
             if not self.pin:
                 return tuple(self.dataset.batch(idx))
+            cur = self._slots[slot]
+            if self._into and cur is not None and cur[0].shape[0] == len(indices):
+                self.dataset.batch_into(idx, cur)          # one pass: gather straight into pinned memory
+                return self._tag(cur, slot)
             fields = self.dataset.batch(idx)
             out = self._slot_like(slot, fields)
             for o, f in zip(out, fields):
                 o.copy_(f)
-            return out
+            return self._tag(out, slot)
         samples = [self.dataset[i] for i in indices]
         fields = tuple(torch.stack([s[k] for s in samples]) for k in range(len(samples[0])))
         if not self.pin:
@@ -78,7 +134,7 @@ class BatchLoader:
         out = self._slot_like(slot, fields)
         for o, f in zip(out, fields):
             o.copy_(f)
-        return out
+        return self._tag(out, slot)
 
 
 class DevicePrefetcher:
@@ -112,8 +168,8 @@ class DevicePrefetcher:
                 self.h2d_bytes += h.numel() * h.element_size()
             self._ready[slot].record(self.copy_stream)
         events = getattr(self.loader, "slot_events", None)
-        if events is not None:
-            host_slot = getattr(self.loader, "last_slot", 0)
+        host_slot = getattr(host, "slot", -1)
+        if events is not None and host_slot >= 0:
             done = torch.cuda.Event()
             done.record(self.copy_stream)
             events[host_slot] = done

@@ -102,8 +102,12 @@ class _PyReducer:
         spec, flat = self.specs[b], self.flats[b]
         with torch.no_grad():
             if spec.total_elems > spec.flags_offset:
-                flags = torch.tensor([1.0 if f else 0.0 for f in self.fired[b]], dtype=flat.dtype)
-                flat[spec.flags_offset:spec.flags_offset + len(self.fired[b])] = flags.to(flat.device)
+                # device-side fills only (no H2D copy): stays legal under CUDA-graph capture
+                lo = spec.flags_offset
+                flat[lo:lo + len(self.fired[b])].fill_(1.0)
+                for k, f in enumerate(self.fired[b]):
+                    if not f:
+                        flat[lo + k:lo + k + 1].zero_()
         self.handles[b] = self.comm.allreduce_async(flat)
         self.launched[b] = True
         self.stats["buckets_launched"] += 1

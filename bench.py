@@ -37,6 +37,8 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+# the image exports NCCL_DEBUG=VERSION, which makes NCCL print a banner on stdout; stdout carries the JSON line
+os.environ["NCCL_DEBUG"] = os.environ.get("B200DDP_NCCL_DEBUG", "WARN")
 BASELINE_PUBLISHED = None   # the reference publishes no number -> vs_baseline = null
 
 MODEL_CHOICES = ("resnet50", "resnet152", "foo", "bert-base")
@@ -57,6 +59,8 @@ def parse_args():
     p.add_argument("--bucket_cap_mb", type=float, default=None)
     p.add_argument("--wire_dtype", type=str, default=None)
     p.add_argument("--skip_e2e", action="store_true")
+    p.add_argument("--no_comm", action="store_true", help="diagnostic: N ranks, gradient communication disabled")
+    p.add_argument("--profile_range", action="store_true", help="cudaProfilerStart/Stop around the device-timed loop (ncu --profile-from-start off)")
     return p.parse_args()
 
 
@@ -197,6 +201,9 @@ def run_ours(args):
                                         gradient_as_bucket_view=False, backend=backend, bucket_cap_mb=args.bucket_cap_mb,
                                         wire_dtype=args.wire_dtype)
         backend = model.backend_name
+        if args.no_comm:
+            model.require_backward_grad_sync = False
+            backend += "(comm disabled: diagnostic)"
     else:
         backend = "single"
     opt = FusedSGD(inner.parameters(), lr=1e-3, max_grad_norm=1000.0)     # after the wrap-time broadcast
@@ -267,6 +274,8 @@ def run_ours(args):
     c0 = C.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
+    if args.profile_range:
+        torch.cuda.profiler.start()
     ev0.record()
     for i in range(args.steps):
         x, y = resident[i % len(resident)]
@@ -274,6 +283,8 @@ def run_ours(args):
         sched.step()
     ev1.record()
     sync_all()
+    if args.profile_range:
+        torch.cuda.profiler.stop()
     eager_launches = C.launch_count() - c0
     ms_dev = ev0.elapsed_time(ev1)
     clocks = sampler_clk.stop() if rank == 0 else {}

@@ -20,15 +20,28 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
-def timed(fn, iters, world, dev):
-    for _ in range(5):
+def timed(fn, iters, world, dev, graph=True):
+    """Device time per call.  The `iters` calls are captured into one CUDA graph and replayed, so the number
+    is the collective itself (kernel + inter-GPU latency), not Python / launch overhead of either stack."""
+    for _ in range(3):
         fn()
+    torch.cuda.synchronize()
+    g = None
+    if graph:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(iters):
+                fn()
+        g.replay()
     dist.barrier(device_ids=[dev.index])
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(iters):
-        fn()
+    if g is not None:
+        g.replay()
+    else:
+        for _ in range(iters):
+            fn()
     e1.record()
     torch.cuda.synchronize()
     t = torch.tensor([e0.elapsed_time(e1) / iters], device=dev, dtype=torch.float64)
@@ -41,7 +54,7 @@ def main():
     ap.add_argument("--max_mb", type=int, default=1024)
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--out", type=str, default=None)
-    ap.add_argument("--blocks", type=str, default="8,16,32,64")
+    ap.add_argument("--blocks", type=str, default="8,32,64,128")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     dev = torch.device("cuda", local)
@@ -69,7 +82,7 @@ def main():
         for wire in ("fp32", "bf16"):
             for algo in algos:
                 for blocks in [int(b) for b in args.blocks.split(",")]:
-                    if size < 65536 and blocks > 8:
+                    if (size < 65536 and blocks > 8) or (size >= (16 << 20) and blocks < 32):
                         continue
 
                     def ours():
