@@ -180,7 +180,25 @@ __global__ void __launch_bounds__(kCommThreads, 1) bucket_allreduce_kernel(const
   }
   peer_block_barrier(c);
 
-  if constexpr (ALGO == kAlgoOneShot) {
+  if constexpr (ALGO == kAlgoNvlsOneShot) {
+    // ---- every rank lets the switch reduce the whole bucket for it: one multimem.ld_reduce per vector,
+    //      no second exchange phase (lowest latency for small buckets)
+    hint = 0;
+    for (uint32_t v = first; v < V; v += U * step) {
+      Vec16 x[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (v + u * step < V) x[u] = W::mc_reduce(c.mc_base + a.stage_off + (size_t)(v + u * step) * 16);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (v + u * step >= V) continue;
+        float f[VE];
+        W::unpack(x[u], f);
+        sq += deliver_vec<InT, VE>(a, slots, offs, (v + u * step) * VE, f, hint);
+      }
+    }
+    peer_block_barrier(c);   // staging may be repacked only after every peer has pulled
+  } else if constexpr (ALGO == kAlgoOneShot) {
     // ---- every rank pulls every vector from every peer and reduces locally
     hint = 0;
     for (uint32_t v = first; v < V; v += step) {
@@ -285,6 +303,7 @@ static void launch_typed(const ArArgs& args, int algo, int blocks, cudaStream_t 
     case kAlgoOneShot: bucket_allreduce_kernel<InT, WireT, kAlgoOneShot><<<blocks, kCommThreads, 0, stream>>>(args); break;
     case kAlgoTwoShot: bucket_allreduce_kernel<InT, WireT, kAlgoTwoShot><<<blocks, kCommThreads, 0, stream>>>(args); break;
     case kAlgoNvls:    bucket_allreduce_kernel<InT, WireT, kAlgoNvls><<<blocks, kCommThreads, 0, stream>>>(args); break;
+    case kAlgoNvlsOneShot: bucket_allreduce_kernel<InT, WireT, kAlgoNvlsOneShot><<<blocks, kCommThreads, 0, stream>>>(args); break;
     default: throw std::runtime_error("bucket_allreduce: unknown algorithm");
   }
 }
@@ -293,7 +312,7 @@ void launch_bucket_allreduce(const CommCtx& ctx, const BucketTable& tab, size_t 
                              DType wire_dtype, int algo, int blocks, void* flat_out, float* sq_partials,
                              float* flags_out, float scale, bool scatter, cudaStream_t stream) {
   if (blocks < 1 || blocks > kMaxCommBlocks) throw std::runtime_error("bucket_allreduce: bad block count");
-  if (algo == kAlgoNvls && ctx.mc_base == nullptr) throw std::runtime_error("bucket_allreduce: NVLS requested without multicast");
+  if ((algo == kAlgoNvls || algo == kAlgoNvlsOneShot) && ctx.mc_base == nullptr) throw std::runtime_error("bucket_allreduce: NVLS requested without multicast");
   if (tab.total_elems % 8 != 0) throw std::runtime_error("bucket_allreduce: bucket not padded to 8 elements");
   ArArgs args;
   args.ctx = ctx;

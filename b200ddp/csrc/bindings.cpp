@@ -186,6 +186,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.attr("ALGO_ONE_SHOT") = (int)kAlgoOneShot;
   m.attr("ALGO_TWO_SHOT") = (int)kAlgoTwoShot;
   m.attr("ALGO_NVLS") = (int)kAlgoNvls;
+  m.attr("ALGO_NVLS_ONE_SHOT") = (int)kAlgoNvlsOneShot;
 
   m.def("launch_count", []() { return (long long)launch_counter().load(); });
   m.def("assign_by_size", &assign_by_size, py::arg("nbytes"), py::arg("keys"), py::arg("limits"), py::arg("max_tensors") = 0);

@@ -9,7 +9,7 @@ namespace b200 {
 struct CommCtx;
 struct BucketTable;
 
-enum : int { kAlgoAuto = -1, kAlgoOneShot = 0, kAlgoTwoShot = 1, kAlgoNvls = 2 };
+enum : int { kAlgoAuto = -1, kAlgoOneShot = 0, kAlgoTwoShot = 1, kAlgoNvls = 2, kAlgoNvlsOneShot = 3 };
 
 // allreduce.cu
 void launch_bucket_allreduce(const CommCtx& ctx, const BucketTable& tab, size_t stage_off, DType in_dtype,

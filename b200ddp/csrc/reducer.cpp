@@ -75,13 +75,15 @@ Reducer::Reducer(PeerArena* arena, std::vector<BucketPlan> plans, int num_params
     // algorithm + grid per bucket (static, so every rank picks the same)
     int algo = opt_.algo;
     if (algo == kAlgoAuto) {
-      if ((long long)wire_bytes <= opt_.one_shot_max_bytes) algo = kAlgoOneShot;
-      else algo = arena_->has_multicast() ? kAlgoNvls : kAlgoTwoShot;
+      const bool mc = arena_->has_multicast();
+      if ((long long)wire_bytes <= opt_.one_shot_max_bytes) algo = mc ? kAlgoNvlsOneShot : kAlgoOneShot;
+      else algo = mc ? kAlgoNvls : kAlgoTwoShot;
     }
     if (algo == kAlgoNvls && !arena_->has_multicast()) algo = kAlgoTwoShot;
+    if (algo == kAlgoNvlsOneShot && !arena_->has_multicast()) algo = kAlgoOneShot;
     s.algo = algo;
     const long long vecs = (long long)(wire_bytes / 16);
-    const long long per_rank = algo == kAlgoOneShot ? vecs : (vecs + ctx_.world - 1) / ctx_.world;
+    const long long per_rank = (algo == kAlgoOneShot || algo == kAlgoNvlsOneShot) ? vecs : (vecs + ctx_.world - 1) / ctx_.world;
     long long blocks = (per_rank + kCommThreads * 4 - 1) / (kCommThreads * 4);
     s.blocks = (int)std::max(1LL, std::min<long long>(blocks, std::min(opt_.max_blocks, kMaxCommBlocks)));
     B200_CUDA_CHECK(cudaEventCreateWithFlags(&s.ready_event, cudaEventDisableTiming));

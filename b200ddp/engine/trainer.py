@@ -26,7 +26,7 @@ from ..data import BatchLoader, DevicePrefetcher, FooDataset, SyntheticImageNet,
 from ..ops import CrossEntropyLoss, MSELoss
 from ..optim import FusedSGD, get_linear_schedule_with_warmup
 from ..parallel import DataParallel, DistributedDataParallel, ShardedSampler
-from ..utils import is_main_process, rng_state, restore_rng_state, to_mixed_bf16
+from ..utils import StepTimer, is_main_process, nvtx_range, rng_state, restore_rng_state, to_mixed_bf16
 from ..utils.checkpoint import latest_checkpoint, load_checkpoint, save_checkpoint
 from .step import TrainStep
 
@@ -135,17 +135,49 @@ class Trainer:
             self._resume_state = load_checkpoint(self.resume_dir, None, self.optimizer, self.scheduler)
             log.info("Resumed from checkpoint.", dict(path=self.resume_dir, global_step=self._resume_state.get("global_step")))
         self.model = model
+        if input_transform is None and self.device.type == "cuda" and getattr(args, "model", "foo").startswith("resnet"):
+            input_transform = self._make_image_transform()
         self.step_fn = TrainStep(model, self.criterion, self.optimizer, self.device,
                                  accumulation=args.gradient_accumulation_steps, use_graph=getattr(args, "cuda_graph", False),
                                  input_transform=input_transform)
         self.global_step = 1
         self.tr_loss_host = 0.0
+        self.timer = StepTimer(self.device, samples_per_step=args.train_batch_size * args.gradient_accumulation_steps * self._world())
+        self.last_throughput = None
 
     # ------------------------------------------------------------------------------------------
+    def _make_image_transform(self):
+        """Raw NCHW batch (fp32 or uint8) -> compute dtype, channels_last when the model is, in ONE kernel
+        (``csrc/input.cu``); writes into the CUDA graph's static input once that exists."""
+        from .. import _ext
+        C = _ext.get()
+        mean = torch.zeros(3, device=self.device)
+        inv_std = torch.ones(3, device=self.device)
+        scratch = {}
+        cl = bool(getattr(self.args, "channels_last", False))
+
+        def transform(x):
+            if x.dim() != 4 or x.dtype not in (torch.float32, torch.uint8) or not x.is_contiguous():
+                return x
+            dst = self.step_fn.static_inputs()[0]
+            if dst is None or dst.shape != x.shape or dst.dtype != self.compute_dtype:
+                dst = scratch.get(tuple(x.shape))
+                if dst is None:
+                    dst = torch.empty(x.shape, dtype=self.compute_dtype, device=self.device)
+                    dst = dst.contiguous(memory_format=torch.channels_last) if cl else dst
+                    scratch[tuple(x.shape)] = dst
+            if not dst.is_contiguous(memory_format=torch.channels_last):
+                return x.to(self.compute_dtype)
+            C.normalize_to_channels_last(x, dst, mean, inv_std, 1.0 / 255.0 if x.dtype == torch.uint8 else 1.0)
+            return dst
+        return transform
+
     def _world(self) -> int:
         return dist.get_world_size() if self.distributed else 1
 
     def _to_compute(self, x: torch.Tensor) -> torch.Tensor:
+        if x.dim() == 4 and self.step_fn.input_transform is not None:
+            return x                       # the fused input kernel casts
         if x.is_floating_point() and x.dtype != self.compute_dtype:
             x = x.to(self.compute_dtype)
         return x
@@ -185,11 +217,13 @@ class Trainer:
                         x, y = x.to(self.device, non_blocking=True), y.to(self.device, non_blocking=True)
                     x, y = self._to_compute(x), self._to_compute(y)
                     boundary = (step + 1) % accum == 0
-                    self.step_fn(x, y, boundary=boundary)
+                    with nvtx_range("train_step"):
+                        self.step_fn(x, y, boundary=boundary)
                     if not boundary:
                         continue
                     self.scheduler.step()
                     self.global_step += 1
+                    self.timer.tick()
 
                     if args.logging_steps > 0 and self.global_step % args.logging_steps == 0:
                         total = self.step_fn.read_loss_sum() + self.tr_loss_host   # the only host sync, every logging_steps
@@ -197,9 +231,14 @@ class Trainer:
                         logging_loss = total
                         if self.show_bars:
                             bar.set_postfix(loss=window)
+                        perf = self.timer.summary()
+                        if perf is not None:
+                            self.last_throughput = perf
                         if self.tb_writer is not None:
                             self.tb_writer.add_scalar("lr", self.scheduler.get_last_lr()[0], self.global_step)
                             self.tb_writer.add_scalar("loss", window, self.global_step)
+                            if perf is not None and "samples_per_s" in perf:
+                                self.tb_writer.add_scalar("samples_per_s", perf["samples_per_s"], self.global_step)
 
                     if args.save_steps > 0 and self.global_step % args.save_steps == 0:
                         self.save(epoch, step + 1 + skip_batches)
@@ -212,8 +251,14 @@ class Trainer:
                 break
         total_loss = self.step_fn.read_loss_sum() + self.tr_loss_host
         elapsed = time.time() - t_start
+        extra = {}
+        if self.last_throughput:
+            extra = {"ms_per_step": round(self.last_throughput["ms_per_step"], 4),
+                     "samples_per_s": round(self.last_throughput.get("samples_per_s", 0.0), 1)}
+        if hasattr(self.model, "ddp_stats"):
+            extra["ddp"] = self.model.ddp_stats()
         log.info("Finished training.", dict(global_step=self.global_step, average_loss=total_loss / self.global_step,
-                                            seconds=round(elapsed, 3)))
+                                            seconds=round(elapsed, 3), **extra))
         if self.tb_writer is not None:
             self.tb_writer.flush()
             self.tb_writer.close()

@@ -25,12 +25,18 @@ class BertConfig:
     type_vocab: int = 2
     eps: float = 1e-12
     dropout: float = 0.0
+    pad_vocab_to: int = 1          # MLM head pads to 64 so logits rows keep the 16-byte pitch TMA needs
+
+    @property
+    def padded_vocab(self) -> int:
+        m = max(1, self.pad_vocab_to)
+        return (self.vocab_size + m - 1) // m * m
 
 
 class BertEmbeddings(nn.Module):
     def __init__(self, c: BertConfig):
         super().__init__()
-        self.word_embeddings = nn.Embedding(c.vocab_size, c.hidden)
+        self.word_embeddings = nn.Embedding(c.padded_vocab, c.hidden)
         self.position_embeddings = nn.Embedding(c.max_position, c.hidden)
         self.token_type_embeddings = nn.Embedding(c.type_vocab, c.hidden)
         self.LayerNorm = LayerNorm(c.hidden, eps=c.eps)
@@ -101,11 +107,12 @@ class BertForMaskedLM(nn.Module):
 
     def __init__(self, config: BertConfig | None = None):
         super().__init__()
+        config = config or BertConfig(pad_vocab_to=64)
         self.bert = BertModel(config, with_pooler=False)
         c = self.bert.config
         self.transform = Linear(c.hidden, c.hidden, activation="gelu")
         self.transform_norm = LayerNorm(c.hidden, eps=c.eps)
-        self.decoder_bias = nn.Parameter(torch.zeros(c.vocab_size))
+        self.decoder_bias = nn.Parameter(torch.zeros(c.padded_vocab))
 
     def forward(self, input_ids, token_type_ids=None, attn_mask=None):
         from ..ops import linear

@@ -22,7 +22,7 @@ from .buckets import BucketSpec
 MiB = 1 << 20
 _DTYPE_CODE = {torch.float32: 0, torch.bfloat16: 1}
 _WIRE_NAME = {"fp32": torch.float32, "float32": torch.float32, "bf16": torch.bfloat16, "bfloat16": torch.bfloat16}
-_ALGO = {"auto": -1, "one_shot": 0, "two_shot": 1, "nvls": 2}
+_ALGO = {"auto": -1, "one_shot": 0, "two_shot": 1, "nvls": 2, "nvls_one_shot": 3}
 
 
 class PeerCommError(RuntimeError):

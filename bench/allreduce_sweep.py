@@ -78,7 +78,8 @@ def main():
         point["nccl_us"] = ms * 1e3
         point["nccl_busbw"] = size / (ms * 1e-3) * 2 * (world - 1) / world / 1e9
         best = None
-        algos = (["one_shot"] if size <= (1 << 20) else []) + ["two_shot"] + (["nvls"] if comm.nvls else [])
+        algos = (["one_shot"] if size <= (1 << 20) else []) + ["two_shot"] + (["nvls"] if comm.nvls else []) + \
+                (["nvls_one_shot"] if comm.nvls and size <= (4 << 20) else [])
         for wire in ("fp32", "bf16"):
             for algo in algos:
                 for blocks in [int(b) for b in args.blocks.split(",")]:

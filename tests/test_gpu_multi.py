@@ -40,14 +40,14 @@ def _check_collectives(rank, world):
     from b200ddp.parallel.peer import PeerCollectives
     dev = torch.device("cuda", rank)
     comm = PeerCollectives.get(None, dev, min_bytes=64 << 20)
-    algos = ["one_shot", "two_shot"] + (["nvls"] if comm.nvls else [])
+    algos = ["one_shot", "two_shot"] + (["nvls", "nvls_one_shot"] if comm.nvls else [])
     print(f"[rank {rank}] nvls={comm.nvls} world={world}", flush=True)
     torch.manual_seed(100 + rank)
     sizes = [1, 7, 165, 4096, 100003, 1 << 20]
     for dtype in (torch.float32, torch.bfloat16):
         for wire in ("fp32", "bf16"):
             for algo in algos:
-                if algo == "one_shot":
+                if algo in ("one_shot", "nvls_one_shot"):
                     use = sizes[:4]
                 else:
                     use = sizes
@@ -202,3 +202,32 @@ def _check_ddp_mlp_bf16_and_unused(rank, world):
 
 def test_ddp_bf16_and_unused_parameters(free_port):
     _spawn(_check_ddp_mlp_bf16_and_unused, free_port)
+
+
+# --------------------------------------------------------------------------------------------------
+def _check_timeout(rank, world):
+    """A peer that never shows up must surface as an error after the timeout, not hang the kernel forever
+    (signal-pad waits need timeouts)."""
+    import time
+    from b200ddp.parallel.peer import PeerCollectives, PeerCommError
+    dev = torch.device("cuda", rank)
+    os.environ["B200DDP_TIMEOUT_S"] = "2"
+    comm = PeerCollectives.get(None, dev, min_bytes=8 << 20)
+    assert comm.timeout_s == 2.0
+    t = torch.ones(1024, device=dev)
+    comm.allreduce_([t], wire="fp32", algo="one_shot")            # healthy collective first
+    torch.cuda.synchronize()
+    comm.check()
+    dist.barrier(device_ids=[rank])
+    if rank == 0:
+        t0 = time.time()
+        comm.allreduce_([t], wire="fp32", algo="one_shot")        # rank 1..n never join this one
+        torch.cuda.synchronize()
+        assert time.time() - t0 < 15
+        with pytest.raises(PeerCommError):
+            comm.check()
+    dist.barrier(device_ids=[rank])
+
+
+def test_missing_peer_times_out_instead_of_hanging(free_port):
+    _spawn(_check_timeout, free_port, world=2)
