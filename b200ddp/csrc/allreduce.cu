@@ -137,19 +137,97 @@ __device__ __forceinline__ float deliver_vec(const ArArgs& a, const TensorSlot* 
   return sq;
 }
 
+
+// Sum the same 16-byte vector over all ranks' staging regions (P2P loads).  PW = compile-time rank count so that
+// 8 / PW vectors x PW peers = 8 independent 16-byte NVLink requests are in flight per thread whatever the world size.
+template <typename W, int PW, int UV>
+__device__ __forceinline__ void pull_and_sum(const CommCtx& c, size_t stage_off, const uint32_t* v_idx, const bool* valid,
+                                             float (*acc)[W::VE]) {
+  Vec16 x[UV][PW];
+#pragma unroll
+  for (int u = 0; u < UV; ++u)
+#pragma unroll
+    for (int p = 0; p < PW; ++p)
+      if (valid[u] && p < c.world) x[u][p] = ld_sys(c.base + (size_t)p * c.stride + stage_off + (size_t)v_idx[u] * 16);
+#pragma unroll
+  for (int u = 0; u < UV; ++u) {
+#pragma unroll
+    for (int i = 0; i < W::VE; ++i) acc[u][i] = 0.f;
+    if (!valid[u]) continue;
+#pragma unroll
+    for (int p = 0; p < PW; ++p)
+      if (p < c.world) {
+        float f[W::VE];
+        W::unpack(x[u][p], f);
+#pragma unroll
+        for (int i = 0; i < W::VE; ++i) acc[u][i] += f[i];
+      }
+  }
+}
+
+template <typename InT, typename W, int PW>
+__device__ __forceinline__ float one_shot_body(const ArArgs& a, const TensorSlot* slots, const uint32_t* offs, uint32_t V,
+                                               uint32_t first, uint32_t step) {
+  constexpr int UV = 8 / PW, VE = W::VE;
+  const CommCtx& c = a.ctx;
+  float sq = 0.f;
+  int hint = 0;
+  for (uint32_t v = first; v < V; v += UV * step) {
+    uint32_t idx[UV];
+    bool valid[UV];
+    float acc[UV][VE];
+#pragma unroll
+    for (int u = 0; u < UV; ++u) { idx[u] = v + u * step; valid[u] = idx[u] < V; }
+    pull_and_sum<W, PW, UV>(c, a.stage_off, idx, valid, acc);
+#pragma unroll
+    for (int u = 0; u < UV; ++u) {
+      if (!valid[u]) continue;
+      // round through the wire format so every algorithm yields the same values
+      Vec16 packed = W::pack(acc[u]);
+      W::unpack(packed, acc[u]);
+      sq += deliver_vec<InT, VE>(a, slots, offs, idx[u] * VE, acc[u], hint);
+    }
+  }
+  return sq;
+}
+
+template <typename W, int PW>
+__device__ __forceinline__ void two_shot_exchange_body(const ArArgs& a, uint32_t base_v, uint32_t lim, uint32_t first, uint32_t step) {
+  constexpr int UV = 8 / PW, VE = W::VE;
+  const CommCtx& c = a.ctx;
+  for (uint32_t j = first; j < lim; j += UV * step) {
+    uint32_t idx[UV];
+    bool valid[UV];
+    float acc[UV][VE];
+#pragma unroll
+    for (int u = 0; u < UV; ++u) { valid[u] = j + u * step < lim; idx[u] = base_v + j + u * step; }
+    pull_and_sum<W, PW, UV>(c, a.stage_off, idx, valid, acc);
+#pragma unroll
+    for (int u = 0; u < UV; ++u) {
+      if (!valid[u]) continue;
+      const Vec16 out = W::pack(acc[u]);
+      const size_t byte_off = a.stage_off + (size_t)idx[u] * 16;
+#pragma unroll
+      for (int p = 0; p < PW; ++p)
+        if (p < c.world) st_sys(c.base + (size_t)p * c.stride + byte_off, out);
+    }
+  }
+}
+
 template <typename InT, typename WireT, int ALGO>
-__global__ void __launch_bounds__(kCommThreads, 1) bucket_allreduce_kernel(const __grid_constant__ ArArgs a) {
+__global__ void __launch_bounds__(kCommThreads, kCommMinCtasPerSm) bucket_allreduce_kernel(const __grid_constant__ ArArgs a) {
   using W = Wire<WireT>;
   constexpr int VE = W::VE;
   __shared__ TensorSlot slots[kMaxBucketTensors];
   __shared__ uint32_t offs[kMaxBucketTensors + 1];
   __shared__ float red[33];
+  __shared__ uint32_t s_epoch;
 
   const CommCtx& c = a.ctx;
   const int P = c.world, r = c.rank, count = a.tab.count;
   for (int i = threadIdx.x; i < count; i += blockDim.x) { slots[i] = a.tab.t[i]; offs[i] = a.tab.t[i].off; }
   if (threadIdx.x == 0) offs[count] = a.tab.data_elems;
-  __syncthreads();
+  const uint32_t epoch = comm_begin(c, &s_epoch);   // also the __syncthreads that publishes slots/offs
 
   const uint32_t V = a.tab.total_elems / VE;
   const uint32_t Vs = (V + P - 1) / P;
@@ -158,7 +236,7 @@ __global__ void __launch_bounds__(kCommThreads, 1) bucket_allreduce_kernel(const
   char* const my_stage = c.base + (size_t)r * c.stride + a.stage_off;
   float sq = 0.f;
   int hint = 0;
-  constexpr int U = 4;    // independent 16-byte requests in flight per thread and loop trip
+  constexpr int U = (sizeof(InT) == 4 && VE == 8) ? 2 : 4;    // independent vector requests in flight per thread and trip
 
   // ---- phase 1: gather + scale + cast into local symmetric staging
   for (int s = 0; s < P; ++s) {
@@ -178,7 +256,7 @@ __global__ void __launch_bounds__(kCommThreads, 1) bucket_allreduce_kernel(const
       }
     }
   }
-  peer_block_barrier(c);
+  peer_block_barrier<kFlagReady>(c, epoch);
 
   if constexpr (ALGO == kAlgoNvlsOneShot) {
     // ---- every rank lets the switch reduce the whole bucket for it: one multimem.ld_reduce per vector,
@@ -197,32 +275,11 @@ __global__ void __launch_bounds__(kCommThreads, 1) bucket_allreduce_kernel(const
         sq += deliver_vec<InT, VE>(a, slots, offs, (v + u * step) * VE, f, hint);
       }
     }
-    peer_block_barrier(c);   // staging may be repacked only after every peer has pulled
   } else if constexpr (ALGO == kAlgoOneShot) {
     // ---- every rank pulls every vector from every peer and reduces locally
-    hint = 0;
-    for (uint32_t v = first; v < V; v += step) {
-      Vec16 x[kMaxRanks];
-#pragma unroll
-      for (int p = 0; p < kMaxRanks; ++p)
-        if (p < P) x[p] = ld_sys(c.base + (size_t)p * c.stride + a.stage_off + (size_t)v * 16);
-      float acc[VE];
-#pragma unroll
-      for (int i = 0; i < VE; ++i) acc[i] = 0.f;
-#pragma unroll
-      for (int p = 0; p < kMaxRanks; ++p)
-        if (p < P) {
-          float f[VE];
-          W::unpack(x[p], f);
-#pragma unroll
-          for (int i = 0; i < VE; ++i) acc[i] += f[i];
-        }
-      // round through the wire format so every algorithm yields the same values
-      Vec16 packed = W::pack(acc);
-      W::unpack(packed, acc);
-      sq += deliver_vec<InT, VE>(a, slots, offs, v * VE, acc, hint);
-    }
-    peer_block_barrier(c);   // nobody may repack its staging while a peer still reads it
+    if (P <= 2) sq += one_shot_body<InT, W, 2>(a, slots, offs, V, first, step);
+    else if (P <= 4) sq += one_shot_body<InT, W, 4>(a, slots, offs, V, first, step);
+    else sq += one_shot_body<InT, W, 8>(a, slots, offs, V, first, step);
   } else {
     // ---- phase 2: reduce-scatter my slice, then all-gather it to every peer
     const uint32_t base_v = (uint32_t)r * Vs;
@@ -238,38 +295,11 @@ __global__ void __launch_bounds__(kCommThreads, 1) bucket_allreduce_kernel(const
           if (j + u * step < lim) multimem_st(c.mc_base + a.stage_off + (size_t)(base_v + j + u * step) * 16, red16[u]);
       }
     } else {
-      constexpr int U2 = 2;
-      for (uint32_t j = first; j < lim; j += U2 * step) {
-        Vec16 x[U2][kMaxRanks];
-#pragma unroll
-        for (int u = 0; u < U2; ++u)
-#pragma unroll
-          for (int p = 0; p < kMaxRanks; ++p)
-            if (p < P && j + u * step < lim)
-              x[u][p] = ld_sys(c.base + (size_t)p * c.stride + a.stage_off + (size_t)(base_v + j + u * step) * 16);
-#pragma unroll
-        for (int u = 0; u < U2; ++u) {
-          if (j + u * step >= lim) continue;
-          float acc[VE];
-#pragma unroll
-          for (int i = 0; i < VE; ++i) acc[i] = 0.f;
-#pragma unroll
-          for (int p = 0; p < kMaxRanks; ++p)
-            if (p < P) {
-              float f[VE];
-              W::unpack(x[u][p], f);
-#pragma unroll
-              for (int i = 0; i < VE; ++i) acc[i] += f[i];
-            }
-          const Vec16 out = W::pack(acc);
-          const size_t byte_off = a.stage_off + (size_t)(base_v + j + u * step) * 16;
-#pragma unroll
-          for (int p = 0; p < kMaxRanks; ++p)
-            if (p < P) st_sys(c.base + (size_t)p * c.stride + byte_off, out);
-        }
-      }
+      if (P <= 2) two_shot_exchange_body<W, 2>(a, base_v, lim, first, step);
+      else if (P <= 4) two_shot_exchange_body<W, 4>(a, base_v, lim, first, step);
+      else two_shot_exchange_body<W, 8>(a, base_v, lim, first, step);
     }
-    peer_block_barrier(c);
+    peer_block_barrier<kFlagSecond>(c, epoch);
     // ---- phase 3: cast back + scatter from local staging
     hint = 0;
     for (int s = 0; s < P; ++s) {
@@ -290,6 +320,9 @@ __global__ void __launch_bounds__(kCommThreads, 1) bucket_allreduce_kernel(const
       }
     }
   }
+
+  // tell every peer this block is finished with their staging; the NEXT launch on this pad set checks it
+  comm_signal_done(c, epoch);
 
   if (a.sq_partials != nullptr) {
     const float total = block_sum(sq, red);

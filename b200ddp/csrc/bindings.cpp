@@ -69,7 +69,7 @@ void allreduce_tensors(PeerArena& arena, const std::vector<at::Tensor>& tensors,
   tab.total_elems = off + (uint32_t)((tab.count + 7) / 8 * 8);
   tab._pad = 0;
   TORCH_CHECK((size_t)tab.total_elems * dtype_size(wire_dt) <= stage_bytes, "allreduce_tensors: staging region too small");
-  CommCtx ctx = make_ctx(arena, (size_t)pad_set * kMaxCommBlocks * kMaxRanks * sizeof(uint32_t), timeout_s);
+  CommCtx ctx = make_ctx(arena, (size_t)pad_set * kPadSetBytes, timeout_s);
   if (algo == kAlgoAuto) algo = arena.has_multicast() ? kAlgoNvls : kAlgoTwoShot;
   float* sq = sq_partials.has_value() ? sq_partials->data_ptr<float>() : nullptr;
   launch_bucket_allreduce(ctx, tab, stage_off, in_dt, wire_dt, algo, blocks, nullptr, sq, nullptr, (float)scale,
@@ -79,7 +79,7 @@ void allreduce_tensors(PeerArena& arena, const std::vector<at::Tensor>& tensors,
 // Broadcast arbitrary tensors from `src`; chunked through the staging region.
 int broadcast_tensors(PeerArena& arena, const std::vector<at::Tensor>& tensors, int src, size_t stage_off,
                       size_t stage_bytes, bool use_mc, int blocks, int pad_set, double timeout_s) {
-  CommCtx ctx = make_ctx(arena, (size_t)pad_set * kMaxCommBlocks * kMaxRanks * sizeof(uint32_t), timeout_s);
+  CommCtx ctx = make_ctx(arena, (size_t)pad_set * kPadSetBytes, timeout_s);
   int launches = 0;
   size_t i = 0;
   const size_t n = tensors.size();
@@ -227,7 +227,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     launch_peer_push(make_ctx(a, 0, 30.0), peer, dst_off, src.data_ptr(), bytes, blocks, cur_stream());
   });
   m.def("peer_barrier", [](PeerArena& a, int blocks, int pad_set, double timeout_s) {
-    launch_peer_barrier(make_ctx(a, (size_t)pad_set * kMaxCommBlocks * kMaxRanks * sizeof(uint32_t), timeout_s), blocks, cur_stream());
+    launch_peer_barrier(make_ctx(a, (size_t)pad_set * kPadSetBytes, timeout_s), blocks, cur_stream());
   }, py::arg("arena"), py::arg("blocks") = 1, py::arg("pad_set") = 1, py::arg("timeout_s") = 30.0);
 
   py::class_<BucketPlan>(m, "BucketPlan")
@@ -242,11 +242,12 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
 
   py::class_<Reducer>(m, "Reducer")
       .def(py::init([](PeerArena& arena, std::vector<BucketPlan> plans, int num_params, int algo,
-                       int max_blocks, long long one_shot_max_bytes, bool as_view, bool find_unused, double extra_scale,
+                       int max_blocks, int tail_blocks, long long one_shot_max_bytes, bool as_view, bool find_unused, double extra_scale,
                        double timeout_s) {
              ReducerOptions o;
              o.algo = algo;
              o.max_blocks = max_blocks;
+             o.tail_blocks = tail_blocks;
              o.one_shot_max_bytes = one_shot_max_bytes;
              o.as_view = as_view;
              o.find_unused = find_unused;

@@ -21,14 +21,15 @@ struct BcArgs {
   BucketTable tab;   // numel/off are BYTES here
 };
 
-__global__ void __launch_bounds__(kCommThreads, 1) peer_broadcast_kernel(const __grid_constant__ BcArgs a) {
+__global__ void __launch_bounds__(kCommThreads, kCommMinCtasPerSm) peer_broadcast_kernel(const __grid_constant__ BcArgs a) {
   __shared__ TensorSlot slots[kMaxBucketTensors];
   __shared__ uint32_t offs[kMaxBucketTensors + 1];
   const CommCtx& c = a.ctx;
   const int count = a.tab.count;
   for (int i = threadIdx.x; i < count; i += blockDim.x) { slots[i] = a.tab.t[i]; offs[i] = a.tab.t[i].off; }
   if (threadIdx.x == 0) offs[count] = a.tab.data_elems;
-  __syncthreads();
+  __shared__ uint32_t s_epoch;
+  const uint32_t epoch = comm_begin(c, &s_epoch);
 
   const uint32_t V = a.tab.total_elems / 16;   // 16-byte vectors
   const uint32_t step = gridDim.x * blockDim.x;
@@ -56,7 +57,7 @@ __global__ void __launch_bounds__(kCommThreads, 1) peer_broadcast_kernel(const _
       else *reinterpret_cast<Vec16*>(stage + (size_t)v * 16) = x;
     }
   }
-  peer_block_barrier(c);
+  peer_block_barrier<kFlagReady>(c, epoch);
   if (!is_src) {
     const char* stage = c.base + (size_t)(a.use_mc ? c.rank : a.src_rank) * c.stride + a.stage_off;
     for (uint32_t v = first; v < V; v += step) {
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(kCommThreads, 1) peer_broadcast_kernel(const _
       }
     }
   }
-  peer_block_barrier(c);
+  comm_signal_done(c, epoch);   // the next chunk may reuse the staging region once every peer has pulled
 }
 
 void launch_peer_broadcast(const CommCtx& ctx, const BucketTable& tab, size_t stage_off, int src_rank,
@@ -116,7 +117,12 @@ __global__ void __launch_bounds__(kCommThreads) peer_push_kernel(const char* __r
     st_sys(dst + v * 16, *reinterpret_cast<const Vec16*>(src + v * 16));
 }
 
-__global__ void __launch_bounds__(kCommThreads) peer_barrier_kernel(const __grid_constant__ CommCtx c) { peer_block_barrier(c); }
+__global__ void __launch_bounds__(kCommThreads) peer_barrier_kernel(const __grid_constant__ CommCtx c) {
+  __shared__ uint32_t s_epoch;
+  const uint32_t epoch = comm_begin(c, &s_epoch);
+  peer_block_barrier<kFlagReady>(c, epoch);
+  comm_signal_done(c, epoch);
+}
 
 void launch_peer_pull(const CommCtx& ctx, int peer, size_t src_off, void* dst, size_t bytes, int blocks, cudaStream_t stream) {
   peer_pull_kernel<<<blocks, kCommThreads, 0, stream>>>(ctx.base + (size_t)peer * ctx.stride + src_off, (char*)dst, bytes / 16);

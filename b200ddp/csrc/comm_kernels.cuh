@@ -7,7 +7,12 @@
 namespace b200 {
 
 constexpr int kMaxBucketTensors = 192;      // keeps the whole launch argument block under 4 KB
-constexpr int kCommThreads = 512;
+// Comm CTAs are deliberately light (256 threads, <= 85 registers/thread -> a third of an SM's register
+// file): they must slot in beside the CTAs of the backward kernels they overlap with instead of
+// evicting them (a 512-thread / 118-register CTA monopolises an SM and turns persistent cuDNN kernels
+// into two waves - measured as "comm time fully exposed", profiles/ddp_overhead_diag_n2_v1.txt).
+constexpr int kCommThreads = 256;
+constexpr int kCommMinCtasPerSm = 3;
 
 // One gradient (or parameter) participating in a flat bucket.
 struct TensorSlot {
@@ -24,11 +29,24 @@ struct BucketTable {
   TensorSlot t[kMaxBucketTensors];
 };
 
+// Signal-pad set: one per staging region (bucket / generic scratch).  All words start at 0.
+//   ready [block][rank] : "rank's block has packed its staging for epoch e"
+//   second[block][rank] : second rendezvous of the same launch (two-shot: results delivered)
+//   done  [block][rank] : "rank's block no longer reads my staging of epoch e" (checked lazily by the NEXT launch)
+//   epoch [block]       : local launch counter (device-resident, so a captured CUDA graph never bakes it)
+struct PadSet {
+  uint32_t ready[kMaxCommBlocks][kMaxRanks];
+  uint32_t second[kMaxCommBlocks][kMaxRanks];
+  uint32_t done[kMaxCommBlocks][kMaxRanks];
+  uint32_t epoch[kMaxCommBlocks];
+};
+static_assert(sizeof(PadSet) <= kPadSetBytes, "pad set does not fit its slot");
+
 struct CommCtx {
   char* base;           // VA of rank 0's arena; rank r at base + r*stride
   char* mc_base;        // multicast VA of the arena (nullptr if NVLS unavailable)
   size_t stride;
-  size_t pad_off;       // byte offset of this communicator's signal pads inside the arena
+  size_t pad_off;       // byte offset of this communicator's PadSet inside the arena
   int* error_word;      // host-mapped; non-zero after a barrier timeout
   unsigned long long timeout_ns;
   int rank, world;
@@ -42,48 +60,72 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 
-// Signal slot protocol (self-resetting, so it is CUDA-graph safe: no epoch argument to bake):
-//   sender: spin CAS 0->1 with release.sys   receiver: spin CAS 1->0 with acquire.sys
-__device__ __forceinline__ uint32_t cas_release_sys(uint32_t* addr, uint32_t cmp, uint32_t val) {
-  uint32_t old;
-  asm volatile("atom.global.release.sys.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(addr), "r"(cmp), "r"(val) : "memory");
-  return old;
+// One-way flags: the sender posts a monotonically increasing epoch with a release store straight into the
+// receiver's memory (fire and forget - no round trip), the receiver polls its OWN memory with acquire loads.
+__device__ __forceinline__ void st_release_sys(uint32_t* addr, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
 }
-__device__ __forceinline__ uint32_t cas_acquire_sys(uint32_t* addr, uint32_t cmp, uint32_t val) {
-  uint32_t old;
-  asm volatile("atom.global.acquire.sys.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(addr), "r"(cmp), "r"(val) : "memory");
-  return old;
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* addr) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(addr) : "memory");
+  return v;
 }
 
-__device__ __forceinline__ bool put_signal(uint32_t* addr, const CommCtx& c) {
-  const unsigned long long t0 = globaltimer_ns();
-  while (cas_release_sys(addr, 0u, 1u) != 0u) {
-    if (globaltimer_ns() - t0 > c.timeout_ns) { *c.error_word = 100 + c.rank; return false; }
-  }
-  return true;
+__device__ __forceinline__ PadSet* pad_of(const CommCtx& c, int rank) {
+  return reinterpret_cast<PadSet*>(c.base + (size_t)rank * c.stride + c.pad_off);
 }
-__device__ __forceinline__ bool wait_signal(uint32_t* addr, const CommCtx& c) {
+
+// wait until *addr >= epoch (wrap-safe), bounded by the timeout
+__device__ __forceinline__ bool wait_epoch(const uint32_t* addr, uint32_t epoch, const CommCtx& c, int code) {
   const unsigned long long t0 = globaltimer_ns();
-  while (cas_acquire_sys(addr, 1u, 0u) != 1u) {
-    if (globaltimer_ns() - t0 > c.timeout_ns) { *c.error_word = 200 + c.rank; return false; }
+  while ((int32_t)(ld_acquire_sys(addr) - epoch) < 0) {
+    if (globaltimer_ns() - t0 > c.timeout_ns) { *c.error_word = code + c.rank; return false; }
   }
   return true;
 }
 
-// Barrier between block `blockIdx.x` of every rank.  Pad layout: [block][sender] uint32.
-// Writes made by any thread of this block before the call are visible to the peer blocks after
-// their call returns (bar.sync -> release.sys ... acquire.sys -> bar.sync).
-__device__ __forceinline__ void peer_block_barrier(const CommCtx& c) {
+// Every launch starts here: fetch + bump this block's epoch, then make sure every peer finished reading
+// the staging region of the PREVIOUS launch on this pad set (it did long ago - this is off the critical path).
+__device__ __forceinline__ uint32_t comm_begin(const CommCtx& c, uint32_t* smem_epoch) {
+  PadSet* mine = pad_of(c, c.rank);
+  if (threadIdx.x == 0) {
+    const uint32_t e = mine->epoch[blockIdx.x] + 1;
+    mine->epoch[blockIdx.x] = e;
+    *smem_epoch = e;
+  }
+  __syncthreads();
+  const uint32_t e = *smem_epoch;
+  if ((int)threadIdx.x < c.world) wait_epoch(&mine->done[blockIdx.x][threadIdx.x], e - 1, c, 300);
+  __syncthreads();
+  return e;
+}
+
+enum : int { kFlagReady = 0, kFlagSecond = 1 };
+
+// Rendezvous of block `blockIdx.x` of every rank.  Writes made by any thread of this block before the call
+// are visible to the peer blocks after their call returns (bar.sync -> st.release.sys ... ld.acquire.sys -> bar.sync).
+template <int WHICH>
+__device__ __forceinline__ void peer_block_barrier(const CommCtx& c, uint32_t epoch) {
   __syncthreads();
   if ((int)threadIdx.x < c.world) {
     const int peer = threadIdx.x;
-    uint32_t* remote = reinterpret_cast<uint32_t*>(c.base + (size_t)peer * c.stride + c.pad_off) +
-                       (size_t)blockIdx.x * kMaxRanks + c.rank;
-    uint32_t* mine = reinterpret_cast<uint32_t*>(c.base + (size_t)c.rank * c.stride + c.pad_off) +
-                     (size_t)blockIdx.x * kMaxRanks + peer;
-    if (put_signal(remote, c)) wait_signal(mine, c);
+    PadSet* theirs = pad_of(c, peer);
+    PadSet* mine = pad_of(c, c.rank);
+    if (WHICH == kFlagReady) {
+      st_release_sys(&theirs->ready[blockIdx.x][c.rank], epoch);
+      wait_epoch(&mine->ready[blockIdx.x][peer], epoch, c, 100);
+    } else {
+      st_release_sys(&theirs->second[blockIdx.x][c.rank], epoch);
+      wait_epoch(&mine->second[blockIdx.x][peer], epoch, c, 200);
+    }
   }
   __syncthreads();
+}
+
+// "I will not read your staging of this epoch any more" - posted, never waited for in this launch.
+__device__ __forceinline__ void comm_signal_done(const CommCtx& c, uint32_t epoch) {
+  __syncthreads();
+  if ((int)threadIdx.x < c.world) st_release_sys(&pad_of(c, threadIdx.x)->done[blockIdx.x][c.rank], epoch);
 }
 
 // ---- 16-byte accessors -----------------------------------------------------------------------

@@ -19,7 +19,8 @@
 
 namespace b200 {
 
-constexpr size_t kSignalBytes = 1 << 20;   // 1 MiB of signal pads at the start of every arena
+constexpr size_t kSignalBytes = 4 << 20;   // 4 MiB of signal pads at the start of every arena
+constexpr size_t kPadSetBytes = 16 << 10;  // one PadSet (comm_kernels.cuh) per staging region -> 256 sets
 constexpr int kMaxRanks = 8;               // one NVSwitch domain (HGX B200)
 constexpr int kMaxCommBlocks = 128;
 

@@ -45,7 +45,7 @@ Reducer::Reducer(PeerArena* arena, std::vector<BucketPlan> plans, int num_params
   ctx_.base = arena_->base();
   ctx_.mc_base = arena_->mc_base();
   ctx_.stride = arena_->stride();
-  ctx_.pad_off = 0;   // reducer kernels own pad set 0 (they are serialised on one stream)
+  ctx_.pad_off = 0;   // per bucket: pad set 2 + bucket index (sets 0/1 belong to the generic collectives)
   ctx_.error_word = arena_->error_word_dev();
   ctx_.timeout_ns = (unsigned long long)(opt_.timeout_s * 1e9);
   ctx_.rank = arena_->rank();
@@ -57,6 +57,7 @@ Reducer::Reducer(PeerArena* arena, std::vector<BucketPlan> plans, int num_params
   for (size_t b = 0; b < plans_.size(); ++b) {
     const BucketPlan& p = plans_[b];
     BucketState& s = buckets_[b];
+    if ((2 + b + 1) * kPadSetBytes > kSignalBytes) throw std::runtime_error("Reducer: too many buckets for the signal-pad area");
     if ((int)p.param_indices.size() > kMaxBucketTensors)
       throw std::runtime_error("Reducer: bucket has more tensors than one launch can carry");
     if (p.total_elems % 8 != 0) throw std::runtime_error("Reducer: bucket not padded to 8 elements");
@@ -84,8 +85,9 @@ Reducer::Reducer(PeerArena* arena, std::vector<BucketPlan> plans, int num_params
     s.algo = algo;
     const long long vecs = (long long)(wire_bytes / 16);
     const long long per_rank = (algo == kAlgoOneShot || algo == kAlgoNvlsOneShot) ? vecs : (vecs + ctx_.world - 1) / ctx_.world;
-    long long blocks = (per_rank + kCommThreads * 4 - 1) / (kCommThreads * 4);
-    s.blocks = (int)std::max(1LL, std::min<long long>(blocks, std::min(opt_.max_blocks, kMaxCommBlocks)));
+    long long blocks = (per_rank + kCommThreads * 8 - 1) / (kCommThreads * 8);
+    const int cap = (b + 1 == plans_.size()) ? opt_.tail_blocks : opt_.max_blocks;
+    s.blocks = (int)std::max(1LL, std::min<long long>(blocks, std::min(cap, kMaxCommBlocks)));
     B200_CUDA_CHECK(cudaEventCreateWithFlags(&s.ready_event, cudaEventDisableTiming));
     B200_CUDA_CHECK(cudaHostAlloc((void**)&s.flags_host, sizeof(float) * kMaxBucketTensors, cudaHostAllocMapped));
     B200_CUDA_CHECK(cudaHostGetDevicePointer((void**)&s.flags_dev, s.flags_host, 0));
@@ -144,7 +146,9 @@ void Reducer::launch_bucket(int b, cudaStream_t compute) {
   float* sq = sq_partials_ ? sq_partials_ + (size_t)b * sq_stride_ : nullptr;
   const float scale = opt_.extra_scale / (float)ctx_.world;
   const bool scatter = !opt_.as_view;
-  launch_bucket_allreduce(ctx_, s.table, s.stage_off, (DType)plans_[b].grad_dtype, (DType)plans_[b].wire_dtype, s.algo, s.blocks,
+  CommCtx ctx = ctx_;
+  ctx.pad_off = (size_t)(2 + b) * kPadSetBytes;
+  launch_bucket_allreduce(ctx, s.table, s.stage_off, (DType)plans_[b].grad_dtype, (DType)plans_[b].wire_dtype, s.algo, s.blocks,
                           (opt_.as_view || opt_.find_unused) ? s.flat_out : nullptr, sq,
                           opt_.find_unused ? s.flags_dev : nullptr, scale, scatter, comm_stream_);
   s.launched = true;

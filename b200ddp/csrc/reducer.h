@@ -39,7 +39,8 @@ struct BucketPlan {
 
 struct ReducerOptions {
   int algo = kAlgoAuto;
-  int max_blocks = 32;
+  int max_blocks = 24;        // CTAs for buckets that overlap with the rest of backward (light: see comm_kernels.cuh)
+  int tail_blocks = 96;       // CTAs for the last bucket of the plan: nothing is left to overlap with, latency is exposed
   long long one_shot_max_bytes = 256 * 1024;
   bool as_view = false;
   bool find_unused = false;

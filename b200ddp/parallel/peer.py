@@ -77,7 +77,8 @@ class PeerCollectives:
             self._setup_multicast()
         self.scratch_off = self.arena.alloc(self.scratch_bytes, 4096)
         self.timeout_s = float(os.environ.get("B200DDP_TIMEOUT_S", "30"))
-        self.blocks = int(os.environ.get("B200DDP_COMM_BLOCKS", "32"))
+        self.blocks = int(os.environ.get("B200DDP_COMM_BLOCKS", "24"))
+        self.tail_blocks = int(os.environ.get("B200DDP_TAIL_BLOCKS", "96"))
         self.closed = False
 
     # ---- bootstrap helpers --------------------------------------------------------------------
@@ -197,7 +198,7 @@ class NativeReducer:
         self._arena_mark = comm.arena.used()
         self._ctor = dict(wire_dtype=wire_dtype, algo=algo, max_blocks=max_blocks)
         one_shot_max = int(os.environ.get("B200DDP_ONE_SHOT_MAX_KB", "256")) * 1024
-        self._c = C.Reducer(comm.arena, plans, len(params), _ALGO[algo], blocks, one_shot_max, gradient_as_bucket_view,
+        self._c = C.Reducer(comm.arena, plans, len(params), _ALGO[algo], blocks, comm.tail_blocks, one_shot_max, gradient_as_bucket_view,
                             find_unused, 1.0, comm.timeout_s)
         device = params[0].device
         self.flat_out: List[Optional[torch.Tensor]] = []
