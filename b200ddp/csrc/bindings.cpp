@@ -238,7 +238,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def_readwrite("data_elems", &BucketPlan::data_elems)
       .def_readwrite("total_elems", &BucketPlan::total_elems)
       .def_readwrite("grad_dtype", &BucketPlan::grad_dtype)
-      .def_readwrite("wire_dtype", &BucketPlan::wire_dtype);
+      .def_readwrite("wire_dtype", &BucketPlan::wire_dtype)
+      .def_readwrite("tail", &BucketPlan::tail);
 
   py::class_<Reducer>(m, "Reducer")
       .def(py::init([](PeerArena& arena, std::vector<BucketPlan> plans, int num_params, int algo,

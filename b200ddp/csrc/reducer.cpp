@@ -86,7 +86,7 @@ Reducer::Reducer(PeerArena* arena, std::vector<BucketPlan> plans, int num_params
     const long long vecs = (long long)(wire_bytes / 16);
     const long long per_rank = (algo == kAlgoOneShot || algo == kAlgoNvlsOneShot) ? vecs : (vecs + ctx_.world - 1) / ctx_.world;
     long long blocks = (per_rank + kCommThreads * 8 - 1) / (kCommThreads * 8);
-    const int cap = (b + 1 == plans_.size()) ? opt_.tail_blocks : opt_.max_blocks;
+    const int cap = (p.tail || b + 1 == plans_.size()) ? opt_.tail_blocks : opt_.max_blocks;
     s.blocks = (int)std::max(1LL, std::min<long long>(blocks, std::min(cap, kMaxCommBlocks)));
     B200_CUDA_CHECK(cudaEventCreateWithFlags(&s.ready_event, cudaEventDisableTiming));
     B200_CUDA_CHECK(cudaHostAlloc((void**)&s.flags_host, sizeof(float) * kMaxBucketTensors, cudaHostAllocMapped));

@@ -35,6 +35,7 @@ struct BucketPlan {
   uint32_t total_elems = 0;
   int grad_dtype = 0;   // DType of this bucket's gradients (buckets are planned per dtype)
   int wire_dtype = 0;   // DType on the wire
+  bool tail = false;    // finishes at the end of backward: gets the wide (tail_blocks) grid
 };
 
 struct ReducerOptions {

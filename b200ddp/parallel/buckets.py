@@ -67,6 +67,7 @@ class BucketSpec:
     flags_offset: int = 0                              # start of the per-tensor "used" flags
     total_elems: int = 0                               # padded data + flags, rounded to align
     key: Hashable = 0
+    tail: bool = False                                 # completes at the very end of backward: latency is exposed
 
     @property
     def data_elems(self) -> int:
@@ -90,7 +91,8 @@ def plan_buckets(numels: Sequence[int], elem_sizes: Sequence[int], keys: Optiona
                  first_bucket_bytes: int = DEFAULT_FIRST_BUCKET_BYTES,
                  order: str = "backward", align: int = SLOT_ALIGN_ELEMS, with_flags: bool = True,
                  ready_order: Optional[Sequence[int]] = None,
-                 max_tensors: int = MAX_TENSORS_PER_BUCKET) -> List[BucketSpec]:
+                 max_tensors: int = MAX_TENSORS_PER_BUCKET, tail_window: int = 4,
+                 tail_bucket_bytes: int = 4 * MiB) -> List[BucketSpec]:
     """Return buckets in LAUNCH order.
 
     order="backward": walk params last-to-first (or ``ready_order`` if observed), first bucket small.
@@ -113,11 +115,42 @@ def plan_buckets(numels: Sequence[int], elem_sizes: Sequence[int], keys: Optiona
                             max_tensors=max_tensors)
     if order == "torch":
         groups = list(reversed(groups))
+    else:
+        # Bound what is exposed at the end of backward: the group that finishes last (per dtype) is cut so its
+        # final piece carries at most `tail_bucket_bytes`; everything before the cut goes out one bucket earlier.
+        if tail_bucket_bytes > 0:
+            sizes = [numels[i] * elem_sizes[i] for i in walk]
+            split = []
+            for grp in groups:
+                is_last_of_key = not any(keys[walk[g2[0]]] == keys[walk[grp[0]]] and max(g2) > max(grp) for g2 in groups)
+                total = sum(sizes[j] for j in grp)
+                if is_last_of_key and total > tail_bucket_bytes and len(grp) > 1:
+                    acc, cut = 0, len(grp)
+                    for pos in range(len(grp) - 1, -1, -1):
+                        acc += sizes[grp[pos]]
+                        if acc > tail_bucket_bytes:
+                            break
+                        cut = pos
+                    cut = min(max(cut, 1), len(grp) - 1)
+                    split += [grp[:cut], grp[cut:]]
+                else:
+                    split.append(grp)
+            groups = split
+        # Launch order = completion order.  A bucket is complete when its LAST gradient (largest walk position)
+        # is ready; with several dtypes in play (bf16 weights + fp32 BatchNorm) the per-dtype groups interleave,
+        # and sorting by first member would park e.g. the all-BatchNorm bucket (finishes at the very end) in
+        # front of buckets that finish early - the in-order launch rule would then hold those back until the
+        # end of backward and expose all of their communication (measured: profiles/ddp_overhead_diag_n2_v2.txt).
+        groups.sort(key=lambda grp: (max(grp), min(grp)))
     specs = []
+    last_positions = set(range(max(0, n - tail_window), n))
     for b, grp in enumerate(groups):
         members = [walk[j] for j in grp]
         spec = BucketSpec(index=b, param_indices=members, numels=[numels[i] for i in members], key=keys[members[0]])
+        spec.tail = order != "torch" and any(j in last_positions for j in grp)
         specs.append(spec.layout(align=align, with_flags=with_flags))
+    if specs:
+        specs[-1].tail = True
     return specs
 
 

@@ -193,6 +193,7 @@ class NativeReducer:
             plan.total_elems = spec.total_elems
             plan.grad_dtype = _DTYPE_CODE[p0.dtype]
             plan.wire_dtype = _DTYPE_CODE[wire]
+            plan.tail = bool(getattr(spec, "tail", False))
             plans.append(plan)
         blocks = max_blocks or comm.blocks
         self._arena_mark = comm.arena.used()

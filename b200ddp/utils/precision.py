@@ -23,12 +23,13 @@ def is_dense(t: torch.Tensor) -> bool:
     """True when the tensor's elements occupy one gap-free block of storage (any permutation of strides)."""
     if t.is_contiguous():
         return True
-    try:
-        from torch._prims_common import is_non_overlapping_and_dense
-        return bool(is_non_overlapping_and_dense(t))
-    except Exception:
-        if t.dim() == 4:
-            return t.is_contiguous(memory_format=torch.channels_last)
-        if t.dim() == 5:
-            return t.is_contiguous(memory_format=torch.channels_last_3d)
-        return False
+    if t.numel() == 0:
+        return True
+    # sort dims by stride; a dense layout has stride[i] == product of the sizes of all faster dims
+    dims = sorted(((st, sz) for st, sz in zip(t.stride(), t.shape) if sz != 1), key=lambda p: p[0])
+    expect = 1
+    for st, sz in dims:
+        if st != expect:
+            return False
+        expect *= sz
+    return True

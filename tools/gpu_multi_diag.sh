@@ -16,6 +16,11 @@ echo "== tests"; timeout 600 python -m pytest tests/test_gpu_multi.py -m gpu -x 
 tail -n 5 $O/test_multi_$N.log
 EXTRA="" run default A=1
 EXTRA="--no_comm" run nocomm A=1
+if [ "$MODE" = "mid" ]; then
+  EXTRA="" run ov8_tail96 B200DDP_COMM_BLOCKS=8
+  EXTRA="" run ov48_tail96 B200DDP_COMM_BLOCKS=48
+  EXTRA="" run ov24_tail24 B200DDP_TAIL_BLOCKS=24
+fi
 if [ "$MODE" = "full" ]; then
   EXTRA="" run ov8_tail96 B200DDP_COMM_BLOCKS=8
   EXTRA="" run ov48_tail96 B200DDP_COMM_BLOCKS=48
@@ -26,6 +31,7 @@ if [ "$MODE" = "full" ]; then
   EXTRA="--backend nccl --no_graph" run nccl_nograph A=1
   EXTRA="--no_graph" run nograph A=1
 fi
+if [ "$MODE" = "mid" ]; then cat $O/diag_summary_$N.txt; exit 0; fi
 echo "== sweep"; timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29601 \
    bench/allreduce_sweep.py --max_mb 256 --out $O/sweep_$N.json > $O/sweep_$N.log 2>&1; echo "sweep rc=$?" | tee -a $O/diag_summary_$N.txt
 tail -n 14 $O/sweep_$N.log
