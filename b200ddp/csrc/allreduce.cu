@@ -23,6 +23,7 @@ struct ArArgs {
   float* flags_out;     // [count] host-mapped, or nullptr
   float scale;
   int scatter;          // write reduced values back into each tensor's own storage
+  int direct;           // the staging region IS the (symmetric) user buffer: no pack / unpack phases
   BucketTable tab;
 };
 
@@ -205,6 +206,10 @@ __device__ __forceinline__ void two_shot_exchange_body(const ArArgs& a, uint32_t
 #pragma unroll
     for (int u = 0; u < UV; ++u) {
       if (!valid[u]) continue;
+      if (a.direct && a.scale != 1.f) {
+#pragma unroll
+        for (int i = 0; i < VE; ++i) acc[u][i] *= a.scale;
+      }
       const Vec16 out = W::pack(acc[u]);
       const size_t byte_off = a.stage_off + (size_t)idx[u] * 16;
 #pragma unroll
@@ -239,7 +244,7 @@ __global__ void __launch_bounds__(kCommThreads, kCommMinCtasPerSm) bucket_allred
   constexpr int U = (sizeof(InT) == 4 && VE == 8) ? 2 : 4;    // independent vector requests in flight per thread and trip
 
   // ---- phase 1: gather + scale + cast into local symmetric staging
-  for (int s = 0; s < P; ++s) {
+  for (int s = 0; s < (a.direct ? 0 : P); ++s) {
     const uint32_t base_v = (uint32_t)s * Vs;
     const uint32_t lim = min(Vs, V > base_v ? V - base_v : 0u);     // vectors of this slice that exist
     for (uint32_t j = first; j < lim; j += U * step) {
@@ -292,7 +297,16 @@ __global__ void __launch_bounds__(kCommThreads, kCommMinCtasPerSm) bucket_allred
           if (j + u * step < lim) red16[u] = W::mc_reduce(c.mc_base + a.stage_off + (size_t)(base_v + j + u * step) * 16);
 #pragma unroll
         for (int u = 0; u < U; ++u)
-          if (j + u * step < lim) multimem_st(c.mc_base + a.stage_off + (size_t)(base_v + j + u * step) * 16, red16[u]);
+          if (j + u * step < lim) {
+            if (a.direct && a.scale != 1.f) {       // in-place symmetric mode: the scale was not applied by a pack phase
+              float f[VE];
+              W::unpack(red16[u], f);
+#pragma unroll
+              for (int i = 0; i < VE; ++i) f[i] *= a.scale;
+              red16[u] = W::pack(f);
+            }
+            multimem_st(c.mc_base + a.stage_off + (size_t)(base_v + j + u * step) * 16, red16[u]);
+          }
       }
     } else {
       if (P <= 2) two_shot_exchange_body<W, 2>(a, base_v, lim, first, step);
@@ -302,7 +316,7 @@ __global__ void __launch_bounds__(kCommThreads, kCommMinCtasPerSm) bucket_allred
     peer_block_barrier<kFlagSecond>(c, epoch);
     // ---- phase 3: cast back + scatter from local staging
     hint = 0;
-    for (int s = 0; s < P; ++s) {
+    for (int s = 0; s < (a.direct ? 0 : P); ++s) {
       const uint32_t bv = (uint32_t)s * Vs;
       const uint32_t ls = min(Vs, V > bv ? V - bv : 0u);
       for (uint32_t j = first; j < ls; j += U * step) {
@@ -341,12 +355,39 @@ static void launch_typed(const ArArgs& args, int algo, int blocks, cudaStream_t 
   }
 }
 
+void launch_symmetric_allreduce(const CommCtx& ctx, size_t buf_off, size_t numel, DType dtype, int algo, int blocks, float scale,
+                                cudaStream_t stream) {
+  if (algo != kAlgoTwoShot && algo != kAlgoNvls) throw std::runtime_error("symmetric allreduce: two_shot or nvls");
+  const size_t ve = dtype == DType::BF16 ? 8 : 4;
+  if (numel % ve != 0 || buf_off % 16 != 0) throw std::runtime_error("symmetric allreduce: buffer must be 16-byte granular");
+  BucketTable tab;
+  tab.count = 0;
+  tab.data_elems = (uint32_t)numel;
+  tab.total_elems = (uint32_t)numel;
+  tab._pad = 0;
+  ArArgs args;
+  args.ctx = ctx;
+  args.stage_off = buf_off;
+  args.flat_out = nullptr;
+  args.sq_partials = nullptr;
+  args.flags_out = nullptr;
+  args.scale = scale;
+  args.scatter = 0;
+  args.direct = 1;
+  args.tab = tab;
+  if (dtype == DType::BF16) launch_typed<__nv_bfloat16, __nv_bfloat16>(args, algo, blocks, stream);
+  else if (dtype == DType::F32) launch_typed<float, float>(args, algo, blocks, stream);
+  else throw std::runtime_error("symmetric allreduce: fp32 or bf16");
+  B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
+}
+
 void launch_bucket_allreduce(const CommCtx& ctx, const BucketTable& tab, size_t stage_off, DType in_dtype,
                              DType wire_dtype, int algo, int blocks, void* flat_out, float* sq_partials,
                              float* flags_out, float scale, bool scatter, cudaStream_t stream) {
   if (blocks < 1 || blocks > kMaxCommBlocks) throw std::runtime_error("bucket_allreduce: bad block count");
   if ((algo == kAlgoNvls || algo == kAlgoNvlsOneShot) && ctx.mc_base == nullptr) throw std::runtime_error("bucket_allreduce: NVLS requested without multicast");
   if (tab.total_elems % 8 != 0) throw std::runtime_error("bucket_allreduce: bucket not padded to 8 elements");
+  if (tab.count < 1) throw std::runtime_error("bucket_allreduce: empty bucket");
   ArArgs args;
   args.ctx = ctx;
   args.stage_off = stage_off;
@@ -355,6 +396,7 @@ void launch_bucket_allreduce(const CommCtx& ctx, const BucketTable& tab, size_t 
   args.flags_out = flags_out;
   args.scale = scale;
   args.scatter = scatter ? 1 : 0;
+  args.direct = 0;
   args.tab = tab;
   const bool in_bf16 = in_dtype == DType::BF16, wire_bf16 = wire_dtype == DType::BF16;
   if (in_dtype != DType::BF16 && in_dtype != DType::F32) throw std::runtime_error("bucket_allreduce: grads must be fp32 or bf16");

@@ -217,6 +217,17 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("allreduce_tensors", &allreduce_tensors, py::arg("arena"), py::arg("tensors"), py::arg("wire") = "bf16",
         py::arg("algo") = (int)kAlgoAuto, py::arg("blocks") = 32, py::arg("stage_off"), py::arg("stage_bytes"),
         py::arg("scale") = 1.0, py::arg("pad_set") = 1, py::arg("timeout_s") = 30.0, py::arg("sq_partials") = py::none());
+  m.def("arena_tensor", [](PeerArena& a, size_t offset, int64_t numel, int dtype_code) {
+    auto dt = dtype_code == 1 ? at::kBFloat16 : dtype_code == 2 ? at::kByte : at::kFloat;
+    auto opts = at::TensorOptions().dtype(dt).device(at::kCUDA, a.device());
+    return at::from_blob(a.local() + offset, {numel}, [](void*) {}, opts);
+  });
+  m.def("allreduce_symmetric", [](PeerArena& a, size_t buf_off, int64_t numel, int dtype_code, int algo, int blocks, double scale,
+                                  int pad_set, double timeout_s) {
+    CommCtx ctx = make_ctx(a, (size_t)pad_set * kPadSetBytes, timeout_s);
+    if (algo == kAlgoAuto) algo = a.has_multicast() ? kAlgoNvls : kAlgoTwoShot;
+    launch_symmetric_allreduce(ctx, buf_off, (size_t)numel, (DType)dtype_code, algo, blocks, (float)scale, cur_stream());
+  });
   m.def("broadcast_tensors", &broadcast_tensors, py::arg("arena"), py::arg("tensors"), py::arg("src") = 0, py::arg("stage_off"),
         py::arg("stage_bytes"), py::arg("use_mc") = false, py::arg("blocks") = 32, py::arg("pad_set") = 1,
         py::arg("timeout_s") = 30.0);

@@ -16,6 +16,10 @@ void launch_bucket_allreduce(const CommCtx& ctx, const BucketTable& tab, size_t 
                              DType wire_dtype, int algo, int blocks, void* flat_out, float* sq_partials,
                              float* flags_out, float scale, bool scatter, cudaStream_t stream);
 
+// in-place allreduce of a buffer that already lives at the same offset in every rank's arena (symmetric memory)
+void launch_symmetric_allreduce(const CommCtx& ctx, size_t buf_off, size_t numel, DType dtype, int algo, int blocks, float scale,
+                                cudaStream_t stream);
+
 // broadcast.cu : `tab` slots are byte ranges (numel/off in BYTES, off multiple of 16)
 void launch_peer_broadcast(const CommCtx& ctx, const BucketTable& tab, size_t stage_off, int src_rank,
                            bool use_multicast, int blocks, cudaStream_t stream);

@@ -20,9 +20,9 @@
 namespace b200 {
 
 constexpr size_t kSignalBytes = 4 << 20;   // 4 MiB of signal pads at the start of every arena
-constexpr size_t kPadSetBytes = 16 << 10;  // one PadSet (comm_kernels.cuh) per staging region -> 256 sets
+constexpr size_t kPadSetBytes = 32 << 10;  // one PadSet (comm_kernels.cuh) per staging region -> 128 sets
 constexpr int kMaxRanks = 8;               // one NVSwitch domain (HGX B200)
-constexpr int kMaxCommBlocks = 128;
+constexpr int kMaxCommBlocks = 296;             // 2 light CTAs per SM on 148 SMs
 
 class PeerArena {
  public:

@@ -155,6 +155,29 @@ class PeerCollectives:
         self.C.allreduce_tensors(self.arena, list(tensors), wire, _ALGO[algo], blocks or self.blocks, self.scratch_off,
                                  self.scratch_bytes, scale, 1, self.timeout_s, None)
 
+    # ---- symmetric memory: tensors that live at the same arena offset on every rank ---------------------
+    def symmetric_empty(self, numel: int, dtype: torch.dtype = torch.float32) -> torch.Tensor:
+        """Allocate a 1-D tensor inside the arena (same call sequence on every rank -> same offset everywhere).
+        Collectives on such tensors run in place over peer memory with no staging copy."""
+        code = _DTYPE_CODE[dtype]
+        nbytes = numel * (2 if dtype == torch.bfloat16 else 4)
+        off = self.arena.alloc((nbytes + 15) // 16 * 16, 4096)
+        t = self.C.arena_tensor(self.arena, off, numel, code)
+        t._b200_arena_off = off
+        return t
+
+    def allreduce_symmetric_(self, t: torch.Tensor, algo: str = "auto", scale: float = 1.0, blocks: Optional[int] = None,
+                             pad_set: int = 0) -> None:
+        if self.world == 1:
+            if scale != 1.0:
+                t.mul_(scale)
+            return
+        off = getattr(t, "_b200_arena_off", None)
+        if off is None:
+            raise ValueError("allreduce_symmetric_ needs a tensor from symmetric_empty()")
+        self.C.allreduce_symmetric(self.arena, off, t.numel(), _DTYPE_CODE[t.dtype], _ALGO[algo], blocks or self.tail_blocks,
+                                   scale, pad_set, self.timeout_s)
+
     def close(self) -> None:
         if not self.closed:
             self.closed = True

@@ -49,19 +49,25 @@ def parse_args():
     p.add_argument("--gpus", type=int, default=1)
     p.add_argument("--steps", type=int, default=30)
     p.add_argument("--warmup", type=int, default=8)
-    p.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
+    p.add_argument("--impl", type=str, default="ours", choices=["ours", "reference", "stock"],
+                   help="ours | reference (unmodified template from baseline/_ref) | stock (torch DDP + NCCL + cuBLAS/cuDNN loop for the non-headline BASELINE configs)")
     p.add_argument("--model", type=str, default="resnet50", choices=MODEL_CHOICES)
-    p.add_argument("--per_gpu_batch", type=int, default=32)
+    p.add_argument("--per_gpu_batch", type=int, default=None, help="default: 32 (resnet/foo, the reference default), 16 (bert-base, seq 512)")
     p.add_argument("--image_size", type=int, default=224)
     p.add_argument("--samples", type=int, default=1024, help="synthetic samples held in host memory per rank")
     p.add_argument("--backend", type=str, default="auto", choices=["auto", "b200", "nccl"])
     p.add_argument("--no_graph", action="store_true")
     p.add_argument("--bucket_cap_mb", type=float, default=None)
     p.add_argument("--wire_dtype", type=str, default=None)
+    p.add_argument("--gradient_as_bucket_view", action="store_true")
+    p.add_argument("--find_unused_parameters", action="store_true")
     p.add_argument("--skip_e2e", action="store_true")
     p.add_argument("--no_comm", action="store_true", help="diagnostic: N ranks, gradient communication disabled")
     p.add_argument("--profile_range", action="store_true", help="cudaProfilerStart/Stop around the device-timed loop (ncu --profile-from-start off)")
-    return p.parse_args()
+    args = p.parse_args()
+    if args.per_gpu_batch is None:
+        args.per_gpu_batch = 16 if args.model.startswith("bert") else 32
+    return args
 
 
 # --------------------------------------------------------------------------------------------------
@@ -197,9 +203,9 @@ def run_ours(args):
     inner = model
     backend = args.backend
     if world > 1:
-        model = DistributedDataParallel(model, device_ids=[local_rank], find_unused_parameters=False,
-                                        gradient_as_bucket_view=False, backend=backend, bucket_cap_mb=args.bucket_cap_mb,
-                                        wire_dtype=args.wire_dtype)
+        model = DistributedDataParallel(model, device_ids=[local_rank], find_unused_parameters=args.find_unused_parameters,
+                                        gradient_as_bucket_view=args.gradient_as_bucket_view, backend=backend,
+                                        bucket_cap_mb=args.bucket_cap_mb, wire_dtype=args.wire_dtype)
         backend = model.backend_name
         if args.no_comm:
             model.require_backward_grad_sync = False
@@ -470,6 +476,85 @@ def run_reference(args):
                       "note": "the reference loop is end to end by construction (DataLoader, blocking .to(device), 2x loss.item())"}})
 
 
+
+# --------------------------------------------------------------------------------------------------
+# stock arm: plain torch DDP + NCCL + library kernels on the same workload (BASELINE configs 3 and 4)
+# --------------------------------------------------------------------------------------------------
+def run_stock(args):
+    import torch
+    import torch.distributed as dist
+    import torch.nn as nn
+    rank, local_rank, world = dist_env()
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group(backend="nccl", device_id=dev)
+    torch.manual_seed(42)
+    torch.backends.cudnn.benchmark = True
+    is_bert = args.model.startswith("bert")
+    if is_bert:
+        from transformers import BertConfig, BertForMaskedLM
+        model = BertForMaskedLM(BertConfig(vocab_size=30528, attn_implementation="sdpa")).to(dev)
+    else:
+        import torchvision
+        model = getattr(torchvision.models, args.model)().to(dev).to(memory_format=torch.channels_last)
+    if world > 1:
+        kw = {}
+        if args.bucket_cap_mb is not None:
+            kw["bucket_cap_mb"] = args.bucket_cap_mb
+        model = nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], gradient_as_bucket_view=args.gradient_as_bucket_view,
+                                                    find_unused_parameters=args.find_unused_parameters, **kw)
+    opt = torch.optim.SGD(model.parameters(), lr=1e-3)
+    B = args.per_gpu_batch
+    if is_bert:
+        xs = [torch.randint(0, 30522, (B, 512), device=dev) for _ in range(4)]
+        ys = [torch.where(torch.rand(B, 512, device=dev) < 0.15, torch.randint(0, 30522, (B, 512), device=dev), torch.full((B, 512), -100, device=dev)) for _ in range(4)]
+    else:
+        xs = [torch.randn(B, 3, args.image_size, args.image_size, device=dev) for _ in range(4)]
+        ys = [torch.zeros(B, 1000, device=dev) for _ in range(4)]
+
+    def one(i):
+        x, y = xs[i % 4], ys[i % 4]
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            if is_bert:
+                loss = model(input_ids=x, labels=y).loss
+            else:
+                out = model(x.contiguous(memory_format=torch.channels_last)).float()
+        if not is_bert:
+            loss = nn.functional.mse_loss(out, y)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1000.0)
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+
+    for i in range(max(args.warmup, 5)):
+        one(i)
+    if world > 1:
+        dist.barrier(device_ids=[local_rank])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        one(i)
+    e1.record()
+    if world > 1:
+        dist.barrier(device_ids=[local_rank])
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+        dist.destroy_process_group()
+    if rank == 0:
+        gb = B * world
+        emit({"metric": f"samples/sec {args.model} DDP bf16", "impl": "stock", "value": gb * args.steps / (ms / 1e3), "unit": "samples/s",
+              "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+              "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic, device-resident",
+              "config": config_dict(args, world, {"transport": "nccl (stock torch DDP)", "bucket_cap_mb": args.bucket_cap_mb,
+                                                  "gradient_as_bucket_view": args.gradient_as_bucket_view,
+                                                  "find_unused_parameters": args.find_unused_parameters})})
+
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -481,6 +566,8 @@ def main():
             rank, _, _ = dist_env()
             if rank == 0:
                 emit({"impl": "reference", "unavailable": f"{type(exc).__name__}: {exc}"[:300]})
+    elif args.impl == "stock":
+        run_stock(args)
     else:
         run_ours(args)
 

@@ -54,7 +54,7 @@ def main():
     ap.add_argument("--max_mb", type=int, default=1024)
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--out", type=str, default=None)
-    ap.add_argument("--blocks", type=str, default="8,32,64,128")
+    ap.add_argument("--blocks", type=str, default="8,32,128,296")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     dev = torch.device("cuda", local)
@@ -62,7 +62,8 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     os.environ.setdefault("B200DDP_SCRATCH_MB", str(args.max_mb + 8))
     from b200ddp.parallel.peer import PeerCollectives
-    comm = PeerCollectives.get(None, dev, min_bytes=0)
+    comm = PeerCollectives.get(None, dev, min_bytes=(args.max_mb + 16) << 20)
+    sym_all = comm.symmetric_empty(args.max_mb * 1024 * 1024 // 4, torch.float32)
     results = {"world": world, "nvls": comm.nvls, "points": []}
     size = 1024
     while size <= args.max_mb * 1024 * 1024:
@@ -98,12 +99,30 @@ def main():
                     if wire == "bf16":
                         point.setdefault("best_bf16wire_busbw", 0.0)
                         point["best_bf16wire_busbw"] = max(point["best_bf16wire_busbw"], bw)
+        # in-place on symmetric memory (no staging copies): the like-for-like comparison with NCCL's in-place allreduce
+        sym = sym_all[:n]
+        sym.normal_()
+        sbest = None
+        for algo in ["two_shot"] + (["nvls"] if comm.nvls else []):
+            for blocks in (8, 32, 64, 128, 296):
+                if (size < 65536 and blocks > 8) or (size >= (16 << 20) and blocks < 64):
+                    continue
+                ms = timed(lambda: comm.allreduce_symmetric_(sym, algo=algo, blocks=blocks), args.iters, world, dev)
+                comm.check()
+                bw = size / (ms * 1e-3) * 2 * (world - 1) / world / 1e9
+                point[f"sym_{algo}_b{blocks}_us"] = ms * 1e3
+                if sbest is None or bw > sbest[1]:
+                    sbest = (f"sym_{algo}_b{blocks}", bw, ms * 1e3)
+        point["best_symmetric"] = sbest[0]
+        point["best_symmetric_busbw"] = sbest[1]
+        point["best_symmetric_us"] = sbest[2]
         point["best_fp32wire"] = best[0]
         point["best_fp32wire_busbw"] = best[1]
         results["points"].append(point)
         if rank == 0:
             print(f"{size:>12d} B  nccl {point['nccl_us']:9.1f} us {point['nccl_busbw']:7.1f} GB/s | ours(fp32 wire) "
-                  f"{best[0]:>22s} {best[1]:7.1f} GB/s | ours(bf16 wire) {point['best_bf16wire_busbw']:7.1f} GB/s", flush=True)
+                  f"{best[0]:>22s} {best[1]:7.1f} GB/s | ours(bf16 wire) {point['best_bf16wire_busbw']:7.1f} GB/s | ours(symmetric in-place) "
+                  f"{sbest[0]:>18s} {sbest[2]:8.1f} us {sbest[1]:7.1f} GB/s", flush=True)
         del bufs
         size *= 4
     if rank == 0 and args.out:

@@ -69,6 +69,20 @@ def _check_collectives(rank, world):
                 gathered = [torch.empty_like(flat) for _ in range(world)]
                 dist.all_gather(gathered, flat)
                 assert all(torch.equal(g, gathered[0]) for g in gathered), (dtype, wire, algo)
+    # in-place allreduce on symmetric (arena-resident) tensors
+    for dtype in (torch.float32, torch.bfloat16):
+        sym = comm.symmetric_empty(40000, dtype)
+        for algo in ["two_shot"] + (["nvls"] if comm.nvls else []):
+            torch.manual_seed(50 + rank)
+            sym.copy_(torch.randn(40000, device=dev).to(dtype))
+            ref = sym.float().clone()
+            dist.all_reduce(ref)
+            dist.barrier(device_ids=[rank])
+            comm.allreduce_symmetric_(sym, algo=algo, scale=1.0 / world)
+            torch.cuda.synchronize()
+            comm.check()
+            tol = 1e-5 if dtype == torch.float32 else 3e-2
+            assert (sym.float() - ref / world).abs().max().item() <= tol * max(1.0, ref.abs().max().item() / world), (dtype, algo)
     # broadcast: odd sizes, unaligned views, several dtypes, a tensor larger than one staging chunk
     torch.manual_seed(7)
     base = [torch.randn(5), torch.randn(1000, 33), torch.randint(0, 100, (77,)), torch.randn(3, 5, 7).to(torch.bfloat16),
