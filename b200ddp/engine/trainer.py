@@ -43,21 +43,26 @@ def _summary_writer():
 
 
 def build_dataset(args):
+    # (loss_kind is defined below; resolved at call time)
     name = getattr(args, "model", "foo")
     n = int(getattr(args, "dataset_size", 100000))
     if name == "foo":
         return FooDataset(n)
     if name.startswith("resnet"):
-        dense = getattr(args, "loss", "mse") == "mse"
+        dense = loss_kind(args) == "mse"
         return SyntheticImageNet(samples=min(n, int(getattr(args, "image_samples", 1024))), dense_target=dense)
     if name.startswith("bert"):
         return SyntheticTokens(samples=min(n, 512), seq_len=int(getattr(args, "seq_len", 512)))
     raise ValueError(f"no default dataset for model {name!r}")
 
 
+def loss_kind(args) -> str:
+    """``--loss`` or the model's default: MSE for the reference's FooModel (``ddp.py:164``), cross-entropy otherwise."""
+    return getattr(args, "loss", None) or ("mse" if getattr(args, "model", "foo") == "foo" else "ce")
+
+
 def build_criterion(args):
-    kind = getattr(args, "loss", None) or ("ce" if getattr(args, "model", "foo").startswith("bert") else "mse")
-    return CrossEntropyLoss() if kind == "ce" else MSELoss()
+    return CrossEntropyLoss() if loss_kind(args) == "ce" else MSELoss()
 
 
 class Trainer:

@@ -98,3 +98,18 @@ def test_torchrun_gloo_two_ranks(tmp_path, free_port):
     assert "[Finished training.] [global_step=13]" in res.stdout
     assert sorted(os.listdir(tmp_path / "o")) == ["checkpoint-12", "checkpoint-6"]
     assert "backend='gloo'" in res.stdout and "world_size=2" in res.stdout
+
+
+def test_default_loss_and_dataset_per_model():
+    import argparse
+    from b200ddp.engine.trainer import build_criterion, build_dataset, loss_kind
+    from b200ddp.ops import CrossEntropyLoss
+    foo = argparse.Namespace(model="foo", loss=None, dataset_size=64)
+    assert loss_kind(foo) == "mse" and isinstance(build_criterion(foo), MSELoss)
+    rn = argparse.Namespace(model="resnet50", loss=None, dataset_size=4, image_samples=4)
+    assert loss_kind(rn) == "ce" and isinstance(build_criterion(rn), CrossEntropyLoss)
+    ds = build_dataset(rn)
+    x, y = ds[0]
+    assert tuple(x.shape) == (3, 224, 224) and y.dtype == torch.int64
+    rn.loss = "mse"
+    assert tuple(build_dataset(rn)[0][1].shape) == (1000,)
