@@ -432,6 +432,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   }, py::arg("a"), py::arg("b"), py::arg("bias") = py::none(), py::arg("a_mn") = false, py::arg("b_mn") = false,
      py::arg("epilogue") = 0, py::arg("out_fp32") = false, py::arg("out") = py::none());
   m.def("gemm_supported", &gemm_shape_supported);
+  m.def("set_gemm_cta_mode", &set_gemm_cta_mode);
 
   // ---- input pipeline ---------------------------------------------------------------------------
   m.def("normalize_to_channels_last", [](at::Tensor src, at::Tensor dst, at::Tensor mean, at::Tensor inv_std, double in_scale) {

@@ -13,5 +13,7 @@ void launch_gemm_bf16(const void* a, const void* b, void* d, const void* bias, i
 void launch_gemm_nt_bf16(const void* a, const void* b, void* d, const void* bias, int M, int N, int K, int epilogue,
                          DType out_dtype, cudaStream_t stream);
 bool gemm_shape_supported(int M, int N, int K, bool a_mn, bool b_mn);
+// 0 = auto (CTA pairs for large problems), 1 = always 1-CTA kernel, 2 = always the cta_group::2 kernel
+void set_gemm_cta_mode(int mode);
 
 }  // namespace b200

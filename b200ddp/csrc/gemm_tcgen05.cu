@@ -18,6 +18,7 @@
 #include "gemm.h"
 
 #include <cuda.h>
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -125,6 +126,56 @@ struct GemmParams {
   void* d;
   const __nv_bfloat16* bias;
 };
+
+// Epilogue for one accumulator row chunk: 32 consecutive columns of row `row` starting at `col0`.
+__device__ __forceinline__ void store_row_chunk(const GemmParams& p, int row, int col0, const uint32_t* r) {
+  if (row < p.M && col0 < p.N) {
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+    if (p.epilogue >= 1 && p.bias != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < p.N) v[i] += __bfloat162float(p.bias[col0 + i]);
+    }
+    if (p.epilogue == 2) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+    } else if (p.epilogue == 3) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+    }
+    const bool full = (col0 + 32 <= p.N);
+    if (p.out_fp32) {
+      float* out = reinterpret_cast<float*>(p.d) + (size_t)row * p.N + col0;
+      if (full && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          if (p.accumulate) { const float4 old = *reinterpret_cast<float4*>(out + i); o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+          *reinterpret_cast<float4*>(out + i) = o;
+        }
+      } else {
+        for (int i = 0; i < 32; ++i)
+          if (col0 + i < p.N) out[i] = p.accumulate ? out[i] + v[i] : v[i];
+      }
+    } else {
+      __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.d) + (size_t)row * p.N + col0;
+      if (full && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          __nv_bfloat162 h[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(v[i + 2 * q], v[i + 2 * q + 1]);
+          *reinterpret_cast<uint4*>(out + i) = *reinterpret_cast<uint4*>(h);
+        }
+      } else {
+        for (int i = 0; i < 32; ++i)
+          if (col0 + i < p.N) out[i] = __float2bfloat16_rn(v[i]);
+      }
+    }
+  }
+}
 
 template <int BLOCK_N, bool A_MN, bool B_MN>
 struct SmemLayout {
@@ -261,53 +312,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         uint32_t r[32];
         tmem_ld32(taddr + (uint32_t)c, r);
         tmem_ld_wait();
-        const int col0 = n0 + c;
-        if (row < p.M && col0 < p.N) {
-          float v[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-          if (p.epilogue >= 1 && p.bias != nullptr) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (col0 + i < p.N) v[i] += __bfloat162float(p.bias[col0 + i]);
-          }
-          if (p.epilogue == 2) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-          } else if (p.epilogue == 3) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
-          }
-          const bool full = (col0 + 32 <= p.N);
-          if (p.out_fp32) {
-            float* out = reinterpret_cast<float*>(p.d) + (size_t)row * p.N + col0;
-            if (full && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 4) {
-                float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                if (p.accumulate) { const float4 old = *reinterpret_cast<float4*>(out + i); o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
-                *reinterpret_cast<float4*>(out + i) = o;
-              }
-            } else {
-              for (int i = 0; i < 32; ++i)
-                if (col0 + i < p.N) out[i] = p.accumulate ? out[i] + v[i] : v[i];
-            }
-          } else {
-            __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.d) + (size_t)row * p.N + col0;
-            if (full && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 8) {
-                __nv_bfloat162 h[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(v[i + 2 * q], v[i + 2 * q + 1]);
-                *reinterpret_cast<uint4*>(out + i) = *reinterpret_cast<uint4*>(h);
-              }
-            } else {
-              for (int i = 0; i < 32; ++i)
-                if (col0 + i < p.N) out[i] = __float2bfloat16_rn(v[i]);
-            }
-          }
-        }
+        store_row_chunk(p, row, n0 + c, r);
       }
       tc_fence_before();
       __syncwarp();
@@ -321,6 +326,192 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// =====================================================================================================
+// 2-CTA variant (cta_group::2): a CTA pair on one TPC computes a 256 x 256 output tile.  Each CTA stages its own
+// 128 rows of A and HALF of the B tile (128 of the 256 N rows); one tcgen05.mma.cta_group::2 issued by the
+// leader CTA reads A/B from both CTAs' shared memory and writes 128 accumulator rows into each CTA's TMEM.
+// Per-CTA shared-memory traffic per MMA halves and a stage is 32 KB instead of 48 KB, so 6 stages fit.
+// =====================================================================================================
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;     // clears the CTA-rank bit of a shared::cluster address -> CTA 0 of the pair
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same smem offset in CTA 0 of the pair (works from either CTA)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint64_t* bar, void* smem, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {   // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+template <bool A_MN, bool B_MN>
+struct SmemLayout2 {
+  static constexpr int BN = 256;                       // pair tile N
+  static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;          // this CTA's 128 rows of A
+  static constexpr int kBBytes = (BN / 2) * BLOCK_K * 2;         // this CTA's half of B
+  static constexpr int kStageBytes = kABytes + kBBytes;          // 32 KB
+  static constexpr int kStages = 6;
+  static constexpr int kTotal = kStages * kStageBytes + 1024 + 1024;
+};
+
+template <bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
+gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmParams p) {
+  using L = SmemLayout2<A_MN, B_MN>;
+  constexpr int BN = L::BN, HALF_N = BN / 2, kStages = L::kStages;
+  constexpr uint32_t kTmemCols = kAccumStages * BN;   // 512
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* barrier_area = smem + kStages * L::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(barrier_area);     // used in the leader CTA only
+  uint64_t* empty_bar = full_bar + kStages;                            // local to each CTA
+  uint64_t* tmem_full_bar = empty_bar + kStages;                       // local to each CTA
+  uint64_t* tmem_empty_bar = tmem_full_bar + kAccumStages;             // used in the leader CTA only
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + kAccumStages);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int num_m_blocks = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+  const int num_n_blocks = (p.N + BN - 1) / BN;
+  const int num_tiles = num_m_blocks * num_n_blocks;
+  const int num_k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
+
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b); }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 2); mbar_init(&empty_bar[i], 1); }      // full: one arrive per CTA
+    for (int i = 0; i < kAccumStages; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 2 * kNumEpilogueWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                      // peer barriers are initialised before anyone signals them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer: every CTA loads its A rows and its half of B =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int m0 = (tile % num_m_blocks) * (2 * BLOCK_M) + (int)cta_rank * BLOCK_M;
+        const int n0 = (tile / num_m_blocks) * BN + (int)cta_rank * HALF_N;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::kStageBytes;
+          uint8_t* sb = sa + L::kABytes;
+          // the leader's barrier collects the bytes of BOTH CTAs; the peer only contributes its arrival
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
+          else mbar_arrive_leader(&full_bar[stage]);
+          const int k0 = kb * BLOCK_K;
+          if constexpr (!A_MN) {
+            tma_load_2d_2sm(&map_a, &full_bar[stage], sa, k0, m0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BLOCK_M / 64; ++c) tma_load_2d_2sm(&map_a, &full_bar[stage], sa + c * (64 * BLOCK_K * 2), m0 + 64 * c, k0);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d_2sm(&map_b, &full_bar[stage], sb, k0, n0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < HALF_N / 64; ++c) tma_load_2d_2sm(&map_b, &full_bar[stage], sb + c * (64 * BLOCK_K * 2), n0 + 64 * c, k0);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: leader CTA only =====================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc(2 * BLOCK_M, BN, A_MN, B_MN);
+      constexpr uint32_t kSbo = 1024;
+      constexpr uint32_t kLboA = A_MN ? BLOCK_K * 128 : 16;
+      constexpr uint32_t kLboB = B_MN ? BLOCK_K * 128 : 16;
+      constexpr uint32_t kStepA = A_MN ? UMMA_K * 128 : UMMA_K * 2;
+      constexpr uint32_t kStepB = B_MN ? UMMA_K * 128 : UMMA_K * 2;
+      int stage = 0;
+      uint32_t phase = 0;
+      int accum = 0;
+      uint32_t accum_phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        mbar_wait(&tmem_empty_bar[accum], accum_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(accum * BN);
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * L::kStageBytes);
+          const uint32_t b_addr = a_addr + L::kABytes;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t da = make_smem_desc(a_addr + k * kStepA, kLboA, kSbo);
+            const uint64_t db = make_smem_desc(b_addr + k * kStepB, kLboB, kSbo);
+            umma_bf16_2sm(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_2sm(&empty_bar[stage]);                        // frees the stage in both CTAs
+          if (kb == num_k_blocks - 1) umma_commit_2sm(&tmem_full_bar[accum]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        if (++accum == kAccumStages) { accum = 0; accum_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: each CTA drains its own 128 accumulator rows =====================
+    const int ew = warp - 4;
+    int accum = 0;
+    uint32_t accum_phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int m0 = (tile % num_m_blocks) * (2 * BLOCK_M) + (int)cta_rank * BLOCK_M;
+      const int n0 = (tile / num_m_blocks) * BN;
+      mbar_wait(&tmem_full_bar[accum], accum_phase);
+      tc_fence_after();
+      const int row = m0 + ew * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(accum * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr + (uint32_t)c, r);
+        tmem_ld_wait();
+        store_row_chunk(p, row, n0 + c, r);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[accum]);
+      if (++accum == kAccumStages) { accum = 0; accum_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                      // nobody frees TMEM / exits while the peer may still signal or read
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
 }
 
@@ -384,7 +575,28 @@ void launch_variant(const void* a, const void* b, const GemmParams& p, cudaStrea
   B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
 }
 
+template <bool A_MN, bool B_MN>
+void launch_variant_2cta(const void* a, const void* b, const GemmParams& p, cudaStream_t stream) {
+  using L = SmemLayout2<A_MN, B_MN>;
+  CUtensorMap map_a = A_MN ? make_map(a, p.K, p.M, BLOCK_K, 64) : make_map(a, p.M, p.K, BLOCK_M, BLOCK_K);
+  CUtensorMap map_b = B_MN ? make_map(b, p.K, p.N, BLOCK_K, 64) : make_map(b, p.N, p.K, L::BN / 2, BLOCK_K);
+  auto kernel = gemm_bf16_2cta_kernel<A_MN, B_MN>;
+  static bool configured = false;
+  if (!configured) {
+    B200_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    configured = true;
+  }
+  const int tiles = ceil_div(p.M, 2 * BLOCK_M) * ceil_div(p.N, L::BN);
+  const int pairs = tiles < kNumSMs / 2 ? tiles : kNumSMs / 2;
+  kernel<<<2 * pairs, kNumThreads, L::kTotal, stream>>>(map_a, map_b, p);     // __cluster_dims__(2,1,1) on the kernel
+  B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
+}
+
+int g_gemm_mode = -1;   // -1 auto, 1 force 1-CTA, 2 force 2-CTA (B200DDP_GEMM_CTAS)
+
 }  // namespace
+
+void set_gemm_cta_mode(int mode) { g_gemm_mode = mode; }
 
 bool gemm_shape_supported(int M, int N, int K, bool a_mn, bool b_mn) {
   if (M < 1 || N < 1 || K < 1) return false;
@@ -407,9 +619,17 @@ void launch_gemm_bf16(const void* a, const void* b, void* d, const void* bias, i
   p.d = d;
   p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
   const bool wide = N > 128;
+  if (g_gemm_mode == -1) {
+    const char* e = getenv("B200DDP_GEMM_CTAS");
+    g_gemm_mode = e ? atoi(e) : 0;
+  }
+  // CTA pairs (cta_group::2) pay off once there is a full 256-row tile per pair and enough tiles to fill 74 pairs
+  const bool pair_ok = M > 128 && N > 128;
+  const bool use_pair = g_gemm_mode == 2 ? true : g_gemm_mode == 1 ? false : (pair_ok && ceil_div(M, 256) * ceil_div(N, 256) >= 37);
 #define B200_GEMM_DISPATCH(AMN, BMN)                                                   \
   if (a_mn == AMN && b_mn == BMN) {                                                    \
-    if (wide) launch_variant<256, AMN, BMN>(a, b, p, stream);                          \
+    if (use_pair) launch_variant_2cta<AMN, BMN>(a, b, p, stream);                      \
+    else if (wide) launch_variant<256, AMN, BMN>(a, b, p, stream);                     \
     else launch_variant<128, AMN, BMN>(a, b, p, stream);                               \
     return;                                                                            \
   }
