@@ -270,6 +270,9 @@ class NativeReducer:
             raise PeerCommError(f"peer-memory barrier timed out (code {code})")
 
     def _finalize_with_unused(self) -> None:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("parameters without gradients were found while capturing a CUDA graph: which parameters "
+                               "are used must be static under --cuda_graph (the reduced 'used' flags need a host read)")
         for b, spec in enumerate(self.specs):
             flags = None
             for k, i in enumerate(spec.param_indices):

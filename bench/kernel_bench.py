@@ -88,9 +88,14 @@ def main():
             a = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
             b = torch.randn(N, K, device=dev, dtype=torch.bfloat16)
             out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
-            ms = timeit(lambda: C.gemm(a, b, None, False, False, 0, False, out), args.iters)
             lib = timeit(lambda: torch.matmul(a, b.t(), out=out), args.iters)
-            record(f"gemm_nt {M}x{N}x{K}", ms, flops=2.0 * M * N * K, lib_ms=lib)
+            for mode, tag in ((1, "1cta"), (2, "2cta")):
+                if mode == 2 and (M <= 128 or N <= 128):
+                    continue
+                C.set_gemm_cta_mode(mode)
+                ms = timeit(lambda: C.gemm(a, b, None, False, False, 0, False, out), args.iters)
+                record(f"gemm_nt[{tag}] {M}x{N}x{K}", ms, flops=2.0 * M * N * K, lib_ms=lib)
+            C.set_gemm_cta_mode(0)
         # backward layouts on the BERT FFN shape
         M, N, K = 16384, 3072, 768
         dy = torch.randn(M, N, device=dev, dtype=torch.bfloat16)
