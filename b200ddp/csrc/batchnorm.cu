@@ -1,0 +1,377 @@
+// Fused training BatchNorm (+ residual add) (+ ReLU) for channels_last activations.
+//
+// Why: in the ResNet-50 bf16 step the stock path (ATen batch_norm_collect_statistics / transform_input /
+// backward_reduce / backward_elemt + separate ReLU, residual-add and threshold_backward kernels + per-layer
+// num_batches_tracked / running-stat updates) is 58% of all kernel time (profiles/launches_graph.md) and runs
+// ~16x below the HBM roofline at batch 32.  A [N,C,H,W] channels_last tensor is a row-major [R = N*H*W, C]
+// matrix, so every per-channel quantity is a column reduction:
+//
+//   forward : bn_stats      column sum / sum-of-squares -> mean, rstd, scale = gamma*rstd, shift = beta - mean*scale,
+//                           running statistics and num_batches_tracked updated by the last block (deterministic)
+//             bn_apply      y = relu(x*scale + shift + residual)            one pass, 16-byte accesses
+//   backward: bn_bwd_reduce sum(dy*), sum(dy* * xhat) with the ReLU mask recomputed from y; dgamma/dbeta
+//             bn_bwd_apply  dx = scale*(dy* - mean(dy*) - xhat*mean(dy* xhat)), and the residual branch's grad
+//
+// Threads own 8 consecutive channels (one 16-byte vector of bf16); rows are strided across the block and
+// across gridDim.y "row splits"; partial sums land in a [splits, C] workspace and the last block of each
+// channel tile finishes the reduction in a fixed order (no float atomics -> bitwise reproducible).
+#include "ops.h"
+
+namespace b200 {
+namespace {
+
+constexpr int kBnThreads = 256;
+constexpr int kVec = 8;              // channels per thread
+
+template <typename T> __device__ __forceinline__ void bn_load8(const T* p, float* f);
+template <> __device__ __forceinline__ void bn_load8<__nv_bfloat16>(const __nv_bfloat16* p, float* f) {
+  unpack8(*reinterpret_cast<const Bf16x8*>(p), f);
+}
+template <> __device__ __forceinline__ void bn_load8<float>(const float* p, float* f) {
+  const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+template <typename T> __device__ __forceinline__ void bn_store8(T* p, const float* f);
+template <> __device__ __forceinline__ void bn_store8<__nv_bfloat16>(__nv_bfloat16* p, const float* f) {
+  *reinterpret_cast<Bf16x8*>(p) = pack8(f);
+}
+template <> __device__ __forceinline__ void bn_store8<float>(float* p, const float* f) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
+}
+
+struct Tile {
+  int cvb;       // channel vectors handled by a block (threads along x)
+  int ty;        // rows handled per block iteration
+  int grid_x;    // channel tiles
+  int grid_y;    // row splits
+};
+
+// Block-level reduction over the `ty` row-lanes of two 8-wide accumulators; result valid for threads with row-lane 0.
+template <int NACC>
+__device__ __forceinline__ void reduce_rows(float (*acc)[kVec], float* smem, int tx, int tyi, int cvb, int ty) {
+  // smem layout: [NACC][ty][cvb*8]
+  const int width = cvb * kVec;
+#pragma unroll
+  for (int a = 0; a < NACC; ++a)
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) smem[(a * ty + tyi) * width + tx * kVec + i] = acc[a][i];
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < NACC * width; idx += blockDim.x) {
+    const int a = idx / width, c = idx % width;
+    float s = 0.f;
+    for (int r = 0; r < ty; ++r) s += smem[(a * ty + r) * width + c];
+    smem[(a * ty) * width + c] = s;       // row-lane 0 slot now holds the block total
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const T* __restrict__ x, int R, int C, int cvb, int ty,
+                                                             float* __restrict__ partial /*[2][S][C]*/, unsigned int* __restrict__ counters,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                             float* __restrict__ running_mean, float* __restrict__ running_var,
+                                                             long long* __restrict__ num_batches, float* __restrict__ save_mean,
+                                                             float* __restrict__ save_rstd, float* __restrict__ scale, float* __restrict__ shift,
+                                                             float eps, float momentum) {
+  extern __shared__ float smem[];
+  __shared__ bool is_last;
+  const int tx = threadIdx.x % cvb, tyi = threadIdx.x / cvb;
+  const int cv = blockIdx.x * cvb + tx;                 // channel-vector index
+  const int S = gridDim.y;
+  const int rows_per = (R + S - 1) / S;
+  const int r0 = blockIdx.y * rows_per, r1 = min(R, r0 + rows_per);
+  float acc[2][kVec];
+#pragma unroll
+  for (int i = 0; i < kVec; ++i) { acc[0][i] = 0.f; acc[1][i] = 0.f; }
+  if (cv * kVec < C) {
+    const T* base = x + (size_t)cv * kVec;
+    int r = r0 + tyi;
+    for (; r + 3 * ty < r1; r += 4 * ty) {              // 4 independent 16-byte loads in flight
+      float f[4][kVec];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) bn_load8<T>(base + (size_t)(r + u * ty) * C, f[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int i = 0; i < kVec; ++i) { acc[0][i] += f[u][i]; acc[1][i] = fmaf(f[u][i], f[u][i], acc[1][i]); }
+    }
+    for (; r < r1; r += ty) {
+      float f[kVec];
+      bn_load8<T>(base + (size_t)r * C, f);
+#pragma unroll
+      for (int i = 0; i < kVec; ++i) { acc[0][i] += f[i]; acc[1][i] = fmaf(f[i], f[i], acc[1][i]); }
+    }
+  }
+  reduce_rows<2>(acc, smem, tx, tyi, cvb, ty);
+  const int width = cvb * kVec;
+  const int c0 = blockIdx.x * width;
+  for (int c = threadIdx.x; c < width; c += blockDim.x) {
+    if (c0 + c < C) {
+      partial[(size_t)(0 * S + blockIdx.y) * C + c0 + c] = smem[c];
+      partial[(size_t)(1 * S + blockIdx.y) * C + c0 + c] = smem[ty * width + c];
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int ticket = atomicAdd(&counters[blockIdx.x], 1u);
+    is_last = (ticket == (unsigned int)S - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const float inv_r = 1.f / (float)R;
+  for (int c = threadIdx.x; c < width; c += blockDim.x) {
+    const int ch = c0 + c;
+    if (ch >= C) continue;
+    float s = 0.f, q = 0.f;
+    for (int k = 0; k < S; ++k) { s += __ldcg(&partial[(size_t)(0 * S + k) * C + ch]); q += __ldcg(&partial[(size_t)(1 * S + k) * C + ch]); }
+    const float mean = s * inv_r;
+    const float var = fmaxf(q * inv_r - mean * mean, 0.f);     // biased variance (normalisation)
+    const float rstd = rsqrtf(var + eps);
+    const float sc = gamma[ch] * rstd;
+    save_mean[ch] = mean;
+    save_rstd[ch] = rstd;
+    scale[ch] = sc;
+    shift[ch] = beta[ch] - mean * sc;
+    if (running_mean != nullptr) {
+      const float unbiased = R > 1 ? var * ((float)R / (float)(R - 1)) : var;
+      running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * mean;
+      running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * unbiased;
+    }
+  }
+  if (threadIdx.x == 0) {
+    counters[blockIdx.x] = 0u;                                   // ready for the next launch (graph replay safe)
+    if (blockIdx.x == 0 && num_batches != nullptr) *num_batches += 1;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ residual, T* __restrict__ y,
+                                                             const float* __restrict__ scale, const float* __restrict__ shift, size_t total_vec,
+                                                             int cv_per_row, int relu) {
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < total_vec; v += (size_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(v % cv_per_row);
+    float f[kVec], sc[kVec], sh[kVec];
+    bn_load8<T>(x + v * kVec, f);
+    bn_load8<float>(scale + cv * kVec, sc);
+    bn_load8<float>(shift + cv * kVec, sh);
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) f[i] = fmaf(f[i], sc[i], sh[i]);
+    if (residual != nullptr) {
+      float rs[kVec];
+      bn_load8<T>(residual + v * kVec, rs);
+#pragma unroll
+      for (int i = 0; i < kVec; ++i) f[i] += rs[i];
+    }
+    if (relu) {
+#pragma unroll
+      for (int i = 0; i < kVec; ++i) f[i] = fmaxf(f[i], 0.f);
+    }
+    bn_store8<T>(y + v * kVec, f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y,
+                                                                  int R, int C, int cvb, int ty, int relu, const float* __restrict__ save_mean,
+                                                                  const float* __restrict__ save_rstd, float* __restrict__ partial,
+                                                                  unsigned int* __restrict__ counters, float* __restrict__ dgamma,
+                                                                  float* __restrict__ dbeta, float* __restrict__ coef /*[2][C]*/) {
+  extern __shared__ float smem[];
+  __shared__ bool is_last;
+  const int tx = threadIdx.x % cvb, tyi = threadIdx.x / cvb;
+  const int cv = blockIdx.x * cvb + tx;
+  const int S = gridDim.y;
+  const int rows_per = (R + S - 1) / S;
+  const int r0 = blockIdx.y * rows_per, r1 = min(R, r0 + rows_per);
+  float acc[2][kVec];
+#pragma unroll
+  for (int i = 0; i < kVec; ++i) { acc[0][i] = 0.f; acc[1][i] = 0.f; }
+  if (cv * kVec < C) {
+    float mean[kVec], rstd[kVec];
+    bn_load8<float>(save_mean + cv * kVec, mean);
+    bn_load8<float>(save_rstd + cv * kVec, rstd);
+    const size_t col = (size_t)cv * kVec;
+    int r = r0 + tyi;
+    for (; r + ty < r1; r += 2 * ty) {                  // 2 rows x 3 streams = 6 independent 16-byte loads in flight
+      float g[2][kVec], xv[2][kVec], yv[2][kVec];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const size_t off = (size_t)(r + u * ty) * C + col;
+        bn_load8<T>(dy + off, g[u]);
+        bn_load8<T>(x + off, xv[u]);
+        if (relu) bn_load8<T>(y + off, yv[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int i = 0; i < kVec; ++i) {
+          const float gm = (relu && !(yv[u][i] > 0.f)) ? 0.f : g[u][i];
+          acc[0][i] += gm;
+          acc[1][i] = fmaf(gm, (xv[u][i] - mean[i]) * rstd[i], acc[1][i]);
+        }
+    }
+    for (; r < r1; r += ty) {
+      float g[kVec], xv[kVec], yv[kVec];
+      const size_t off = (size_t)r * C + col;
+      bn_load8<T>(dy + off, g);
+      bn_load8<T>(x + off, xv);
+      if (relu) bn_load8<T>(y + off, yv);
+#pragma unroll
+      for (int i = 0; i < kVec; ++i) {
+        const float gm = (relu && !(yv[i] > 0.f)) ? 0.f : g[i];
+        acc[0][i] += gm;
+        acc[1][i] = fmaf(gm, (xv[i] - mean[i]) * rstd[i], acc[1][i]);
+      }
+    }
+  }
+  reduce_rows<2>(acc, smem, tx, tyi, cvb, ty);
+  const int width = cvb * kVec;
+  const int c0 = blockIdx.x * width;
+  for (int c = threadIdx.x; c < width; c += blockDim.x) {
+    if (c0 + c < C) {
+      partial[(size_t)(0 * S + blockIdx.y) * C + c0 + c] = smem[c];
+      partial[(size_t)(1 * S + blockIdx.y) * C + c0 + c] = smem[ty * width + c];
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int ticket = atomicAdd(&counters[blockIdx.x], 1u);
+    is_last = (ticket == (unsigned int)S - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const float inv_r = 1.f / (float)R;
+  for (int c = threadIdx.x; c < width; c += blockDim.x) {
+    const int ch = c0 + c;
+    if (ch >= C) continue;
+    float s = 0.f, q = 0.f;
+    for (int k = 0; k < S; ++k) { s += __ldcg(&partial[(size_t)(0 * S + k) * C + ch]); q += __ldcg(&partial[(size_t)(1 * S + k) * C + ch]); }
+    dbeta[ch] = s;
+    dgamma[ch] = q;
+    coef[ch] = s * inv_r;            // mean(dy*)
+    coef[C + ch] = q * inv_r;        // mean(dy* xhat)
+  }
+  if (threadIdx.x == 0) counters[blockIdx.x] = 0u;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y,
+                                                                 T* __restrict__ dx, T* __restrict__ dres, const float* __restrict__ save_mean,
+                                                                 const float* __restrict__ save_rstd, const float* __restrict__ gamma,
+                                                                 const float* __restrict__ coef, size_t total_vec, int cv_per_row, int C, int relu) {
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < total_vec; v += (size_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(v % cv_per_row);
+    float g[kVec], xv[kVec], mean[kVec], rstd[kVec], gam[kVec], c1[kVec], c2[kVec];
+    bn_load8<T>(dy + v * kVec, g);
+    bn_load8<T>(x + v * kVec, xv);
+    if (relu) {
+      float yv[kVec];
+      bn_load8<T>(y + v * kVec, yv);
+#pragma unroll
+      for (int i = 0; i < kVec; ++i) g[i] = yv[i] > 0.f ? g[i] : 0.f;
+    }
+    bn_load8<float>(save_mean + cv * kVec, mean);
+    bn_load8<float>(save_rstd + cv * kVec, rstd);
+    bn_load8<float>(gamma + cv * kVec, gam);
+    bn_load8<float>(coef + cv * kVec, c1);
+    bn_load8<float>(coef + C + cv * kVec, c2);
+    if (dres != nullptr) bn_store8<T>(dres + v * kVec, g);          // gradient of the residual branch = masked dy
+    float o[kVec];
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) {
+      const float xhat = (xv[i] - mean[i]) * rstd[i];
+      o[i] = gam[i] * rstd[i] * (g[i] - c1[i] - xhat * c2[i]);
+    }
+    bn_store8<T>(dx + v * kVec, o);
+  }
+}
+
+Tile pick_tile(int R, int C) {
+  Tile t;
+  const int cv = C / kVec;
+  t.cvb = cv < 32 ? cv : 32;
+  while (kBnThreads % t.cvb != 0) --t.cvb;            // threads along x must divide the block
+  t.ty = kBnThreads / t.cvb;
+  t.grid_x = (cv + t.cvb - 1) / t.cvb;
+  // enough row splits to put ~4 blocks on every SM, but keep >= 4 row iterations per block
+  int want = (4 * kNumSMs + t.grid_x - 1) / t.grid_x;
+  int max_by_rows = R / (t.ty * 4);
+  if (max_by_rows < 1) max_by_rows = 1;
+  t.grid_y = want < max_by_rows ? want : max_by_rows;
+  if (t.grid_y > 1024) t.grid_y = 1024;
+  return t;
+}
+
+int apply_blocks(size_t total_vec) {
+  size_t b = (total_vec + kBnThreads * 4 - 1) / (kBnThreads * 4);
+  if (b > (size_t)kNumSMs * 16) b = (size_t)kNumSMs * 16;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace
+
+void bn_workspace_sizes(int R, int C, size_t* partial_floats, size_t* counters) {
+  const Tile t = pick_tile(R, C);
+  *partial_floats = (size_t)2 * t.grid_y * C;
+  *counters = (size_t)t.grid_x;
+}
+
+void launch_bn_forward(const void* x, const void* residual, void* y, DType dt, int R, int C, const float* gamma, const float* beta,
+                       float* running_mean, float* running_var, long long* num_batches, float* save_mean, float* save_rstd,
+                       float* scale, float* shift, float* partial, unsigned int* counters, float eps, float momentum, bool relu,
+                       cudaStream_t s) {
+  if (C % kVec != 0) throw std::runtime_error("fused batch norm: channel count must be a multiple of 8");
+  const Tile t = pick_tile(R, C);
+  const size_t smem = (size_t)2 * t.ty * t.cvb * kVec * sizeof(float);
+  const dim3 grid(t.grid_x, t.grid_y);
+  const size_t total_vec = (size_t)R * (C / kVec);
+  if (dt == DType::BF16) {
+    bn_stats_kernel<__nv_bfloat16><<<grid, kBnThreads, smem, s>>>((const __nv_bfloat16*)x, R, C, t.cvb, t.ty, partial, counters, gamma, beta,
+                                                                  running_mean, running_var, num_batches, save_mean, save_rstd, scale, shift, eps, momentum);
+    B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
+    bn_apply_kernel<__nv_bfloat16><<<apply_blocks(total_vec), kBnThreads, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)residual,
+                                                                                  (__nv_bfloat16*)y, scale, shift, total_vec, C / kVec, relu ? 1 : 0);
+  } else {
+    bn_stats_kernel<float><<<grid, kBnThreads, smem, s>>>((const float*)x, R, C, t.cvb, t.ty, partial, counters, gamma, beta, running_mean,
+                                                          running_var, num_batches, save_mean, save_rstd, scale, shift, eps, momentum);
+    B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
+    bn_apply_kernel<float><<<apply_blocks(total_vec), kBnThreads, 0, s>>>((const float*)x, (const float*)residual, (float*)y, scale, shift,
+                                                                          total_vec, C / kVec, relu ? 1 : 0);
+  }
+  B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
+}
+
+void launch_bn_backward(const void* dy, const void* x, const void* y, void* dx, void* dres, DType dt, int R, int C, const float* gamma,
+                        const float* save_mean, const float* save_rstd, float* dgamma, float* dbeta, float* coef, float* partial,
+                        unsigned int* counters, bool relu, cudaStream_t s) {
+  if (C % kVec != 0) throw std::runtime_error("fused batch norm: channel count must be a multiple of 8");
+  const Tile t = pick_tile(R, C);
+  const size_t smem = (size_t)2 * t.ty * t.cvb * kVec * sizeof(float);
+  const dim3 grid(t.grid_x, t.grid_y);
+  const size_t total_vec = (size_t)R * (C / kVec);
+  if (dt == DType::BF16) {
+    bn_bwd_reduce_kernel<__nv_bfloat16><<<grid, kBnThreads, smem, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, R, C,
+                                                                       t.cvb, t.ty, relu ? 1 : 0, save_mean, save_rstd, partial, counters, dgamma, dbeta, coef);
+    B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
+    bn_bwd_apply_kernel<__nv_bfloat16><<<apply_blocks(total_vec), kBnThreads, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,
+                                                                                      (const __nv_bfloat16*)y, (__nv_bfloat16*)dx, (__nv_bfloat16*)dres,
+                                                                                      save_mean, save_rstd, gamma, coef, total_vec, C / kVec, C, relu ? 1 : 0);
+  } else {
+    bn_bwd_reduce_kernel<float><<<grid, kBnThreads, smem, s>>>((const float*)dy, (const float*)x, (const float*)y, R, C, t.cvb, t.ty, relu ? 1 : 0,
+                                                               save_mean, save_rstd, partial, counters, dgamma, dbeta, coef);
+    B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
+    bn_bwd_apply_kernel<float><<<apply_blocks(total_vec), kBnThreads, 0, s>>>((const float*)dy, (const float*)x, (const float*)y, (float*)dx,
+                                                                              (float*)dres, save_mean, save_rstd, gamma, coef, total_vec, C / kVec, C, relu ? 1 : 0);
+  }
+  B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
+}
+
+}  // namespace b200

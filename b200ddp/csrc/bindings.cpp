@@ -434,6 +434,59 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm_supported", &gemm_shape_supported);
   m.def("set_gemm_cta_mode", &set_gemm_cta_mode);
 
+  // ---- fused BatchNorm ---------------------------------------------------------------------------
+  m.def("bn_workspace", [](int R, int C) {
+    size_t pf = 0, cn = 0;
+    bn_workspace_sizes(R, C, &pf, &cn);
+    return std::make_tuple((long long)pf, (long long)cn);
+  });
+  m.def("bn_forward", [](at::Tensor x, c10::optional<at::Tensor> residual, at::Tensor gamma, at::Tensor beta,
+                         c10::optional<at::Tensor> running_mean, c10::optional<at::Tensor> running_var,
+                         c10::optional<at::Tensor> num_batches, double eps, double momentum, bool relu, at::Tensor partial,
+                         at::Tensor counters) {
+    check_cuda(x, "x");
+    TORCH_CHECK(x.dim() == 4 && x.is_contiguous(at::MemoryFormat::ChannelsLast), "bn_forward: x must be 4-D channels_last");
+    TORCH_CHECK(gamma.scalar_type() == at::kFloat && beta.scalar_type() == at::kFloat, "bn_forward: fp32 affine parameters");
+    c10::cuda::CUDAGuard guard(x.device());
+    const int C = (int)x.size(1);
+    const int R = (int)(x.numel() / C);
+    at::Tensor y = at::empty_like(x);
+    auto fopt = x.options().dtype(at::kFloat);
+    at::Tensor stats = at::empty({4, C}, fopt);   // rows: save_mean, save_rstd, scale, shift
+    const void* res = nullptr;
+    if (residual.has_value()) {
+      TORCH_CHECK(residual->sizes() == x.sizes() && residual->dtype() == x.dtype() && residual->is_contiguous(at::MemoryFormat::ChannelsLast),
+                  "bn_forward: residual must match x (shape, dtype, channels_last)");
+      res = residual->data_ptr();
+    }
+    float* st = stats.data_ptr<float>();
+    launch_bn_forward(x.data_ptr(), res, y.data_ptr(), dtype_of(x), R, C, gamma.data_ptr<float>(), beta.data_ptr<float>(),
+                      running_mean.has_value() ? running_mean->data_ptr<float>() : nullptr,
+                      running_var.has_value() ? running_var->data_ptr<float>() : nullptr,
+                      num_batches.has_value() ? (long long*)num_batches->data_ptr<int64_t>() : nullptr, st, st + C, st + 2 * C, st + 3 * C,
+                      partial.data_ptr<float>(), (unsigned int*)counters.data_ptr<int>(), (float)eps, (float)momentum, relu, cur_stream());
+    return std::make_tuple(y, stats);
+  });
+  m.def("bn_backward", [](at::Tensor dy, at::Tensor x, c10::optional<at::Tensor> y, at::Tensor gamma, at::Tensor stats, bool relu,
+                          bool need_dres, at::Tensor partial, at::Tensor counters) {
+    check_cuda(dy, "dy");
+    c10::cuda::CUDAGuard guard(x.device());
+    const int C = (int)x.size(1);
+    const int R = (int)(x.numel() / C);
+    at::Tensor dyc = dy.is_contiguous(at::MemoryFormat::ChannelsLast) ? dy : dy.contiguous(at::MemoryFormat::ChannelsLast);
+    at::Tensor dx = at::empty_like(x);
+    at::Tensor dres = need_dres ? at::empty_like(x) : at::Tensor();
+    auto fopt = x.options().dtype(at::kFloat);
+    at::Tensor dparams = at::empty({4, C}, fopt);   // rows: dgamma, dbeta, coef1, coef2
+    float* dp = dparams.data_ptr<float>();
+    const float* st = stats.data_ptr<float>();
+    TORCH_CHECK(!relu || y.has_value(), "bn_backward: the ReLU mask needs the saved output");
+    launch_bn_backward(dyc.data_ptr(), x.data_ptr(), relu ? y->data_ptr() : nullptr, dx.data_ptr(), need_dres ? dres.data_ptr() : nullptr,
+                       dtype_of(x), R, C, gamma.data_ptr<float>(), st, st + C, dp, dp + C, dp + 2 * C, partial.data_ptr<float>(),
+                       (unsigned int*)counters.data_ptr<int>(), relu, cur_stream());
+    return std::make_tuple(dx, dres, dparams);
+  });
+
   // ---- input pipeline ---------------------------------------------------------------------------
   m.def("normalize_to_channels_last", [](at::Tensor src, at::Tensor dst, at::Tensor mean, at::Tensor inv_std, double in_scale) {
     check_cuda(src, "src"); check_cuda(dst, "dst");

@@ -9,7 +9,7 @@ from typing import List
 import torch
 import torch.nn as nn
 
-from ..ops import Linear
+from ..ops import FusedBatchNormAct2d, Linear
 
 
 class Bottleneck(nn.Module):
@@ -17,21 +17,20 @@ class Bottleneck(nn.Module):
 
     def __init__(self, inplanes: int, planes: int, stride: int = 1, downsample: nn.Module | None = None):
         super().__init__()
+        # BatchNorm + ReLU (and, for bn3, the shortcut add) are single fused kernels on channels_last CUDA tensors
         self.conv1 = nn.Conv2d(inplanes, planes, 1, bias=False)
-        self.bn1 = nn.BatchNorm2d(planes)
+        self.bn1 = FusedBatchNormAct2d(planes, relu=True)
         self.conv2 = nn.Conv2d(planes, planes, 3, stride=stride, padding=1, bias=False)
-        self.bn2 = nn.BatchNorm2d(planes)
+        self.bn2 = FusedBatchNormAct2d(planes, relu=True)
         self.conv3 = nn.Conv2d(planes, planes * self.expansion, 1, bias=False)
-        self.bn3 = nn.BatchNorm2d(planes * self.expansion)
-        self.relu = nn.ReLU(inplace=True)
+        self.bn3 = FusedBatchNormAct2d(planes * self.expansion, relu=True)
         self.downsample = downsample
 
     def forward(self, x):
         identity = x if self.downsample is None else self.downsample(x)
-        out = self.relu(self.bn1(self.conv1(x)))
-        out = self.relu(self.bn2(self.conv2(out)))
-        out = self.bn3(self.conv3(out))
-        return self.relu(out + identity)
+        out = self.bn1(self.conv1(x))
+        out = self.bn2(self.conv2(out))
+        return self.bn3(self.conv3(out), residual=identity)
 
 
 class ResNet(nn.Module):
@@ -39,8 +38,7 @@ class ResNet(nn.Module):
         super().__init__()
         self.inplanes = 64
         self.conv1 = nn.Conv2d(3, 64, 7, stride=2, padding=3, bias=False)
-        self.bn1 = nn.BatchNorm2d(64)
-        self.relu = nn.ReLU(inplace=True)
+        self.bn1 = FusedBatchNormAct2d(64, relu=True)
         self.maxpool = nn.MaxPool2d(3, stride=2, padding=1)
         self.layer1 = self._make_layer(64, layers[0], 1)
         self.layer2 = self._make_layer(128, layers[1], 2)
@@ -63,14 +61,14 @@ class ResNet(nn.Module):
         downsample = None
         if stride != 1 or self.inplanes != planes * Bottleneck.expansion:
             downsample = nn.Sequential(nn.Conv2d(self.inplanes, planes * Bottleneck.expansion, 1, stride=stride, bias=False),
-                                       nn.BatchNorm2d(planes * Bottleneck.expansion))
+                                       FusedBatchNormAct2d(planes * Bottleneck.expansion))
         mods = [Bottleneck(self.inplanes, planes, stride, downsample)]
         self.inplanes = planes * Bottleneck.expansion
         mods += [Bottleneck(self.inplanes, planes) for _ in range(1, blocks)]
         return nn.Sequential(*mods)
 
     def forward(self, x):
-        x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
+        x = self.maxpool(self.bn1(self.conv1(x)))
         x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
         x = torch.flatten(self.avgpool(x), 1)
         return self.fc(x)
