@@ -618,18 +618,29 @@ void launch_gemm_bf16(const void* a, const void* b, void* d, const void* bias, i
   p.accumulate = accumulate ? 1 : 0;
   p.d = d;
   p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
-  const bool wide = N > 128;
   if (g_gemm_mode == -1) {
     const char* e = getenv("B200DDP_GEMM_CTAS");
     g_gemm_mode = e ? atoi(e) : 0;
   }
-  // CTA pairs (cta_group::2) pay off once there is a full 256-row tile per pair and enough tiles to fill 74 pairs
-  const bool pair_ok = M > 128 && N > 128;
-  const bool use_pair = g_gemm_mode == 2 ? true : g_gemm_mode == 1 ? false : (pair_ok && ceil_div(M, 256) * ceil_div(N, 256) >= 37);
+  // Tile-shape choice by wave quantisation: cost = waves x per-tile work x a measured inefficiency factor of the
+  // configuration (CTA pairs feed the tensor pipe best; 128x128 single-CTA tiles are shared-memory-bandwidth bound).
+  auto waves = [](long long tiles, long long slots) { return (tiles + slots - 1) / slots; };
+  const double cost_pair = (double)waves((long long)ceil_div(M, 256) * ceil_div(N, 256), kNumSMs / 2) * 256.0 * 256.0 * 1.00;
+  const double cost_wide = (double)waves((long long)ceil_div(M, 128) * ceil_div(N, 256), kNumSMs) * 128.0 * 256.0 * 1.12;
+  const double cost_sq = (double)waves((long long)ceil_div(M, 128) * ceil_div(N, 128), kNumSMs) * 128.0 * 128.0 * 1.30;
+  int choice;   // 0 = pair 256x256, 1 = single 128x256, 2 = single 128x128
+  if (g_gemm_mode == 2) choice = 0;
+  else if (g_gemm_mode == 1) choice = (N > 128) ? 1 : 2;
+  else {
+    choice = 2;
+    double best = cost_sq;
+    if (N > 128 && cost_wide < best) { best = cost_wide; choice = 1; }
+    if (M > 128 && N > 128 && cost_pair < best) { best = cost_pair; choice = 0; }
+  }
 #define B200_GEMM_DISPATCH(AMN, BMN)                                                   \
   if (a_mn == AMN && b_mn == BMN) {                                                    \
-    if (use_pair) launch_variant_2cta<AMN, BMN>(a, b, p, stream);                      \
-    else if (wide) launch_variant<256, AMN, BMN>(a, b, p, stream);                     \
+    if (choice == 0) launch_variant_2cta<AMN, BMN>(a, b, p, stream);                   \
+    else if (choice == 1) launch_variant<256, AMN, BMN>(a, b, p, stream);              \
     else launch_variant<128, AMN, BMN>(a, b, p, stream);                               \
     return;                                                                            \
   }

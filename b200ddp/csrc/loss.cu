@@ -9,6 +9,19 @@ namespace {
 
 constexpr int kLossThreads = 256;
 
+template <typename T> __device__ __forceinline__ void loss_load8(const T* p, float* f);
+template <> __device__ __forceinline__ void loss_load8<__nv_bfloat16>(const __nv_bfloat16* p, float* f) { unpack8(*reinterpret_cast<const Bf16x8*>(p), f); }
+template <> __device__ __forceinline__ void loss_load8<float>(const float* p, float* f) {
+  const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+template <typename T> __device__ __forceinline__ void loss_store8(T* p, const float* f);
+template <> __device__ __forceinline__ void loss_store8<__nv_bfloat16>(__nv_bfloat16* p, const float* f) { *reinterpret_cast<Bf16x8*>(p) = pack8(f); }
+template <> __device__ __forceinline__ void loss_store8<float>(float* p, const float* f) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kLossThreads) mse_fwd_bwd_kernel(const T* __restrict__ out, const T* __restrict__ tgt, size_t n,
                                                                    float gscale, float* __restrict__ loss, T* __restrict__ dout,
@@ -18,7 +31,32 @@ __global__ void __launch_bounds__(kLossThreads) mse_fwd_bwd_kernel(const T* __re
   const float inv_n = 1.f / (float)n;
   const float k = 2.f * inv_n * gscale;
   float acc = 0.f;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(tgt) | reinterpret_cast<uintptr_t>(dout)) & 31u) == 0;
+  size_t done = 0;
+  if (aligned) {
+    const size_t nvec = n / 8;
+    size_t v = tid;
+    for (; v + stride < nvec; v += 2 * stride) {            // two independent vector pairs in flight
+      float a0[8], b0[8], a1[8], b1[8];
+      loss_load8<T>(out + v * 8, a0); loss_load8<T>(tgt + v * 8, b0);
+      loss_load8<T>(out + (v + stride) * 8, a1); loss_load8<T>(tgt + (v + stride) * 8, b1);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { a0[i] -= b0[i]; acc = fmaf(a0[i], a0[i], acc); a0[i] *= k; a1[i] -= b1[i]; acc = fmaf(a1[i], a1[i], acc); a1[i] *= k; }
+      loss_store8<T>(dout + v * 8, a0);
+      loss_store8<T>(dout + (v + stride) * 8, a1);
+    }
+    for (; v < nvec; v += stride) {
+      float a0[8], b0[8];
+      loss_load8<T>(out + v * 8, a0); loss_load8<T>(tgt + v * 8, b0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { a0[i] -= b0[i]; acc = fmaf(a0[i], a0[i], acc); a0[i] *= k; }
+      loss_store8<T>(dout + v * 8, a0);
+    }
+    done = nvec * 8;
+  }
+  for (size_t i = done + tid; i < n; i += stride) {
     const float d = to_f32<T>(out[i]) - to_f32<T>(tgt[i]);
     acc += d * d;
     dout[i] = from_f32<T>(k * d);
@@ -72,6 +110,73 @@ __global__ void __launch_bounds__(kLossThreads) xent_fwd_bwd_kernel(const T* __r
   }
 }
 
+// Row lives in shared memory: ONE global read of the logits, softmax statistics and the gradient come from smem,
+// ONE global write of dlogits; 16-byte accesses with a peeled head/tail (rows of a 30522-wide matrix are only
+// 4-byte aligned).  smem index = column + pad so shared and global addresses share their 16-byte phase.
+template <typename T>
+__global__ void __launch_bounds__(kLossThreads) xent_fwd_bwd_smem_kernel(const T* __restrict__ logits, const long long* __restrict__ targets,
+                                                                         int rows, int cols, long long ignore_index, float gscale,
+                                                                         float* __restrict__ row_loss, T* __restrict__ dlogits) {
+  extern __shared__ __align__(16) unsigned char xsmem[];
+  __shared__ float red[33];
+  constexpr int EPV = 16 / sizeof(T);                   // elements per 16-byte vector
+  const int row = blockIdx.x;
+  const T* x = logits + (size_t)row * cols;
+  T* dx = dlogits + (size_t)row * cols;
+  const int pad = (int)((reinterpret_cast<uintptr_t>(x) & 15u) / sizeof(T));
+  T* sx = reinterpret_cast<T*>(xsmem);                   // sx[pad + i] = x[i]
+  const int head = min(cols, (EPV - pad) % EPV);         // scalars until the first aligned vector
+  const int nvec = (cols - head) / EPV;
+  const int tail0 = head + nvec * EPV;
+  const long long t = targets[row];
+  const bool ignored = (t == ignore_index) || t < 0 || t >= cols;
+
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < head; i += blockDim.x) { const T v = x[i]; sx[pad + i] = v; m = fmaxf(m, to_f32<T>(v)); }
+  for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(x + head + v * EPV);
+    *reinterpret_cast<uint4*>(sx + pad + head + v * EPV) = raw;
+    const T* e = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+    for (int j = 0; j < EPV; ++j) m = fmaxf(m, to_f32<T>(e[j]));
+  }
+  for (int i = tail0 + threadIdx.x; i < cols; i += blockDim.x) { const T v = x[i]; sx[pad + i] = v; m = fmaxf(m, to_f32<T>(v)); }
+  m = block_max(m, red);                                 // (contains the __syncthreads that publishes smem)
+  float s = 0.f;
+  for (int i = threadIdx.x; i < cols; i += blockDim.x) s += __expf(to_f32<T>(sx[pad + i]) - m);
+  s = block_sum(s, red);
+  const float lse = m + __logf(s);
+  const float valid = row_loss[rows];
+  if (threadIdx.x == 0) row_loss[row] = ignored ? 0.f : lse - to_f32<T>(sx[pad + (int)t]);
+  const float g = (ignored || valid <= 0.f) ? 0.f : gscale / valid;
+  const float coef = g / s;
+  const int ti = ignored ? -1 : (int)t;
+  for (int i = threadIdx.x; i < head; i += blockDim.x) {
+    float p = __expf(to_f32<T>(sx[pad + i]) - m) * coef;
+    if (i == ti) p -= g;
+    dx[i] = from_f32<T>(p);
+  }
+  for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+    const int base = head + v * EPV;
+    const uint4 raw = *reinterpret_cast<const uint4*>(sx + pad + base);
+    const T* e = reinterpret_cast<const T*>(&raw);
+    uint4 outv;
+    T* o = reinterpret_cast<T*>(&outv);
+#pragma unroll
+    for (int j = 0; j < EPV; ++j) {
+      float p = __expf(to_f32<T>(e[j]) - m) * coef;
+      if (base + j == ti) p -= g;
+      o[j] = from_f32<T>(p);
+    }
+    *reinterpret_cast<uint4*>(dx + base) = outv;
+  }
+  for (int i = tail0 + threadIdx.x; i < cols; i += blockDim.x) {
+    float p = __expf(to_f32<T>(sx[pad + i]) - m) * coef;
+    if (i == ti) p -= g;
+    dx[i] = from_f32<T>(p);
+  }
+}
+
 __global__ void __launch_bounds__(1024) xent_finish_kernel(const float* __restrict__ row_loss, const long long* __restrict__ targets,
                                                            int rows, int cols, long long ignore_index, float* __restrict__ loss) {
   __shared__ float red[33];
@@ -100,9 +205,9 @@ __global__ void __launch_bounds__(1024) count_valid_kernel(const long long* __re
 }  // namespace
 
 int mse_blocks(size_t n) {
-  size_t b = (n + kLossThreads * 8 - 1) / (kLossThreads * 8);
+  size_t b = (n + kLossThreads * 16 - 1) / (kLossThreads * 16);
   if (b < 1) b = 1;
-  if (b > 2 * kNumSMs) b = 2 * kNumSMs;
+  if (b > 8 * kNumSMs) b = 8 * kNumSMs;
   return (int)b;
 }
 
@@ -123,7 +228,24 @@ void launch_xent_fwd_bwd(const void* logits, const long long* targets, DType dt,
   // one carries the count) so no host round trip is needed.
   const float g = gscale;
   count_valid_kernel<<<1, 1024, 0, s>>>(targets, rows, cols, ignore_index, row_loss + rows);
-  if (dt == DType::BF16)
+  const size_t esz = dt == DType::BF16 ? 2 : 4;
+  const size_t smem = ((size_t)cols + 16) * esz;
+  if (smem <= 200 * 1024 && ((reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(dlogits)) % esz) == 0 &&
+      (reinterpret_cast<uintptr_t>(logits) & 15u) == (reinterpret_cast<uintptr_t>(dlogits) & 15u)) {
+    // dlogits rows must share the 16-byte phase of the logits rows (both come from the same allocator: they do)
+    static bool configured = false;
+    if (!configured) {
+      B200_CUDA_CHECK(cudaFuncSetAttribute(xent_fwd_bwd_smem_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      B200_CUDA_CHECK(cudaFuncSetAttribute(xent_fwd_bwd_smem_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      configured = true;
+    }
+    if (dt == DType::BF16)
+      xent_fwd_bwd_smem_kernel<__nv_bfloat16><<<rows, kLossThreads, smem, s>>>((const __nv_bfloat16*)logits, targets, rows, cols, ignore_index, g,
+                                                                             row_loss, (__nv_bfloat16*)dlogits);
+    else
+      xent_fwd_bwd_smem_kernel<float><<<rows, kLossThreads, smem, s>>>((const float*)logits, targets, rows, cols, ignore_index, g, row_loss,
+                                                                     (float*)dlogits);
+  } else if (dt == DType::BF16)
     xent_fwd_bwd_kernel<__nv_bfloat16><<<rows, kLossThreads, 0, s>>>((const __nv_bfloat16*)logits, targets, rows, cols, ignore_index, g,
                                                                    row_loss, (__nv_bfloat16*)dlogits);
   else

@@ -90,6 +90,12 @@ class BatchLoader:
                 yield item
         finally:
             stop.set()
+            try:                      # unblock a producer waiting on a full queue, then wait for it to leave native code
+                while True:
+                    q.get_nowait()
+            except queue.Empty:
+                pass
+            t.join(timeout=2.0)
 
     def _produce(self) -> Iterator[Tuple[torch.Tensor, ...]]:
         indices: List[int] = []

@@ -352,6 +352,7 @@ def run_ours(args):
                           "ms_per_step": e2e["ms"] / args.steps, "h2d_bytes_per_step": e2e["h2d"],
                           "d2h_bytes_per_step": e2e["d2h"], "last_loss": e2e["last_loss"]}
         emit(out)
+    stream.close()                      # stops the loader's helper thread before interpreter shutdown
     if world > 1:
         try:
             from b200ddp.parallel.peer import PeerCollectives

@@ -53,7 +53,7 @@ def timeit(fn, iters=20, flush=True):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", type=str, default="gemm,sgd,ln,xent,mse,input")
+    ap.add_argument("--only", type=str, default="gemm,bn,sgd,ln,xent,mse,input")
     ap.add_argument("--out", type=str, default=None)
     ap.add_argument("--iters", type=int, default=20)
     args = ap.parse_args()
@@ -111,6 +111,28 @@ def main():
         ms = timeit(lambda: C.gemm(x, w, bias, False, False, 3, False, None), args.iters)
         lib = timeit(lambda: torch.nn.functional.gelu(torch.nn.functional.linear(x, w, bias)), args.iters)
         record(f"gemm+bias+gelu {M}x{N}x{K}", ms, flops=2.0 * M * N * K, lib_ms=lib, note="lib = cuBLAS linear + gelu kernel")
+
+    if "bn" in want:
+        from b200ddp.ops import FusedBatchNormAct2d
+        for shape in [(32, 64, 112, 112), (32, 256, 56, 56), (32, 64, 56, 56), (32, 512, 28, 28), (32, 1024, 14, 14), (32, 2048, 7, 7)]:
+            x = torch.randn(*shape, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            res = torch.randn_like(x)
+            nbytes = x.numel() * 2
+            bn = FusedBatchNormAct2d(shape[1], relu=True).to(dev)
+            ref = torch.nn.BatchNorm2d(shape[1]).to(dev)
+            ws = bn._workspace(x)
+            fwd = lambda: C.bn_forward(x, res, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked, 1e-5, 0.1, True, ws[0], ws[1])
+            ms = timeit(fwd, args.iters)
+            lib = timeit(lambda: torch.relu(ref(x) + res), args.iters)
+            record(f"bn+add+relu fwd {shape}", ms, bytes_=nbytes * 4, lib_ms=lib, note="min traffic: x read twice (2nd from L2), res, y")
+            y, stats = fwd()
+            dy = torch.randn_like(x)
+            ms = timeit(lambda: C.bn_backward(dy, x, y, bn.weight, stats, True, True, ws[2], ws[3]), args.iters)
+            xr = x.clone().requires_grad_()
+            rr = res.clone().requires_grad_()
+            yl = torch.relu(ref(xr) + rr)
+            lib = timeit(lambda: torch.autograd.grad(yl, (xr, rr), dy, retain_graph=True), args.iters)
+            record(f"bn+add+relu bwd {shape}", ms, bytes_=nbytes * 8, lib_ms=lib, note="reads dy,x,y twice; writes dx,dres")
 
     if "sgd" in want:
         for dtype, label in ((torch.float32, "fp32"), (torch.bfloat16, "bf16+master")):

@@ -18,7 +18,7 @@ def _rel_err(a, b):
 
 
 @pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
-@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (512, 512, 256), (1000, 1000, 2048), (4096, 3072, 768), (300, 264, 72), (8192, 768, 3072)])
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (512, 512, 256), (1000, 1000, 2048), (4096, 3072, 768), (304, 264, 72), (8192, 768, 3072)])
 def test_gemm_2cta_matches_reference_and_1cta(C, a_mn, b_mn, M, N, K):
     torch.manual_seed(0)
     A = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
