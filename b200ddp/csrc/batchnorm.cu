@@ -123,11 +123,25 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const T* __restric
   if (!is_last) return;
   __threadfence();
   const float inv_r = 1.f / (float)R;
+  // finish: `lanes` threads per channel each sum a strided subset of the S partials (independent loads in flight),
+  // then a fixed-order combine through shared memory
+  const int lanes = max(1, (int)blockDim.x / width);
+  {
+    const int c = threadIdx.x % width, l = threadIdx.x / width;
+    float ps = 0.f, pq = 0.f;
+    if (l < lanes && c0 + c < C) {
+#pragma unroll 4
+      for (int k = l; k < S; k += lanes) { ps += __ldcg(&partial[(size_t)(0 * S + k) * C + c0 + c]); pq += __ldcg(&partial[(size_t)(1 * S + k) * C + c0 + c]); }
+    }
+    __syncthreads();
+    if (l < lanes) { smem[l * width + c] = ps; smem[(lanes + l) * width + c] = pq; }
+    __syncthreads();
+  }
   for (int c = threadIdx.x; c < width; c += blockDim.x) {
     const int ch = c0 + c;
     if (ch >= C) continue;
     float s = 0.f, q = 0.f;
-    for (int k = 0; k < S; ++k) { s += __ldcg(&partial[(size_t)(0 * S + k) * C + ch]); q += __ldcg(&partial[(size_t)(1 * S + k) * C + ch]); }
+    for (int l = 0; l < lanes; ++l) { s += smem[l * width + c]; q += smem[(lanes + l) * width + c]; }
     const float mean = s * inv_r;
     const float var = fmaxf(q * inv_r - mean * mean, 0.f);     // biased variance (normalisation)
     const float rstd = rsqrtf(var + eps);
@@ -150,27 +164,48 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const T* __restric
 
 template <typename T>
 __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ residual, T* __restrict__ y,
-                                                             const float* __restrict__ scale, const float* __restrict__ shift, size_t total_vec,
-                                                             int cv_per_row, int relu) {
-  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < total_vec; v += (size_t)gridDim.x * blockDim.x) {
-    const int cv = (int)(v % cv_per_row);
-    float f[kVec], sc[kVec], sh[kVec];
-    bn_load8<T>(x + v * kVec, f);
-    bn_load8<float>(scale + cv * kVec, sc);
-    bn_load8<float>(shift + cv * kVec, sh);
+                                                             const float* __restrict__ scale, const float* __restrict__ shift, int R, int C,
+                                                             int cvb, int ty, int relu) {
+  const int tx = threadIdx.x % cvb, tyi = threadIdx.x / cvb;
+  const int cv = blockIdx.x * cvb + tx;
+  if (cv * kVec >= C) return;
+  const int S = gridDim.y;
+  const int rows_per = (R + S - 1) / S;
+  const int r0 = blockIdx.y * rows_per, r1 = min(R, r0 + rows_per);
+  float sc[kVec], sh[kVec];                       // per-channel constants stay in registers for the whole row loop
+  bn_load8<float>(scale + cv * kVec, sc);
+  bn_load8<float>(shift + cv * kVec, sh);
+  const size_t col = (size_t)cv * kVec;
+  int r = r0 + tyi;
+  for (; r + 3 * ty < r1; r += 4 * ty) {
+    float f[4][kVec], rs[4][kVec];
 #pragma unroll
-    for (int i = 0; i < kVec; ++i) f[i] = fmaf(f[i], sc[i], sh[i]);
-    if (residual != nullptr) {
-      float rs[kVec];
-      bn_load8<T>(residual + v * kVec, rs);
-#pragma unroll
-      for (int i = 0; i < kVec; ++i) f[i] += rs[i];
+    for (int u = 0; u < 4; ++u) {
+      bn_load8<T>(x + (size_t)(r + u * ty) * C + col, f[u]);
+      if (residual != nullptr) bn_load8<T>(residual + (size_t)(r + u * ty) * C + col, rs[u]);
     }
-    if (relu) {
 #pragma unroll
-      for (int i = 0; i < kVec; ++i) f[i] = fmaxf(f[i], 0.f);
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int i = 0; i < kVec; ++i) {
+        float v = fmaf(f[u][i], sc[i], sh[i]);
+        if (residual != nullptr) v += rs[u][i];
+        f[u][i] = relu ? fmaxf(v, 0.f) : v;
+      }
+      bn_store8<T>(y + (size_t)(r + u * ty) * C + col, f[u]);
     }
-    bn_store8<T>(y + v * kVec, f);
+  }
+  for (; r < r1; r += ty) {
+    float f[kVec], rs[kVec];
+    bn_load8<T>(x + (size_t)r * C + col, f);
+    if (residual != nullptr) bn_load8<T>(residual + (size_t)r * C + col, rs);
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) {
+      float v = fmaf(f[i], sc[i], sh[i]);
+      if (residual != nullptr) v += rs[i];
+      f[i] = relu ? fmaxf(v, 0.f) : v;
+    }
+    bn_store8<T>(y + (size_t)r * C + col, f);
   }
 }
 
@@ -248,11 +283,25 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(const T* __re
   if (!is_last) return;
   __threadfence();
   const float inv_r = 1.f / (float)R;
+  // finish: `lanes` threads per channel each sum a strided subset of the S partials (independent loads in flight),
+  // then a fixed-order combine through shared memory
+  const int lanes = max(1, (int)blockDim.x / width);
+  {
+    const int c = threadIdx.x % width, l = threadIdx.x / width;
+    float ps = 0.f, pq = 0.f;
+    if (l < lanes && c0 + c < C) {
+#pragma unroll 4
+      for (int k = l; k < S; k += lanes) { ps += __ldcg(&partial[(size_t)(0 * S + k) * C + c0 + c]); pq += __ldcg(&partial[(size_t)(1 * S + k) * C + c0 + c]); }
+    }
+    __syncthreads();
+    if (l < lanes) { smem[l * width + c] = ps; smem[(lanes + l) * width + c] = pq; }
+    __syncthreads();
+  }
   for (int c = threadIdx.x; c < width; c += blockDim.x) {
     const int ch = c0 + c;
     if (ch >= C) continue;
     float s = 0.f, q = 0.f;
-    for (int k = 0; k < S; ++k) { s += __ldcg(&partial[(size_t)(0 * S + k) * C + ch]); q += __ldcg(&partial[(size_t)(1 * S + k) * C + ch]); }
+    for (int l = 0; l < lanes; ++l) { s += smem[l * width + c]; q += smem[(lanes + l) * width + c]; }
     dbeta[ch] = s;
     dgamma[ch] = q;
     coef[ch] = s * inv_r;            // mean(dy*)
@@ -265,39 +314,74 @@ template <typename T>
 __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y,
                                                                  T* __restrict__ dx, T* __restrict__ dres, const float* __restrict__ save_mean,
                                                                  const float* __restrict__ save_rstd, const float* __restrict__ gamma,
-                                                                 const float* __restrict__ coef, size_t total_vec, int cv_per_row, int C, int relu) {
-  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < total_vec; v += (size_t)gridDim.x * blockDim.x) {
-    const int cv = (int)(v % cv_per_row);
-    float g[kVec], xv[kVec], mean[kVec], rstd[kVec], gam[kVec], c1[kVec], c2[kVec];
-    bn_load8<T>(dy + v * kVec, g);
-    bn_load8<T>(x + v * kVec, xv);
-    if (relu) {
-      float yv[kVec];
-      bn_load8<T>(y + v * kVec, yv);
-#pragma unroll
-      for (int i = 0; i < kVec; ++i) g[i] = yv[i] > 0.f ? g[i] : 0.f;
-    }
+                                                                 const float* __restrict__ coef, int R, int C, int cvb, int ty, int relu) {
+  const int tx = threadIdx.x % cvb, tyi = threadIdx.x / cvb;
+  const int cv = blockIdx.x * cvb + tx;
+  if (cv * kVec >= C) return;
+  const int S = gridDim.y;
+  const int rows_per = (R + S - 1) / S;
+  const int r0 = blockIdx.y * rows_per, r1 = min(R, r0 + rows_per);
+  // dx = a*dy* + b*x + c  with per-channel a = gamma*rstd, b = -a*rstd*c2, c = -a*(c1 - mean*rstd*c2)
+  float ka[kVec], kb[kVec], kc[kVec];
+  {
+    float mean[kVec], rstd[kVec], gam[kVec], c1[kVec], c2[kVec];
     bn_load8<float>(save_mean + cv * kVec, mean);
     bn_load8<float>(save_rstd + cv * kVec, rstd);
     bn_load8<float>(gamma + cv * kVec, gam);
     bn_load8<float>(coef + cv * kVec, c1);
     bn_load8<float>(coef + C + cv * kVec, c2);
-    if (dres != nullptr) bn_store8<T>(dres + v * kVec, g);          // gradient of the residual branch = masked dy
-    float o[kVec];
 #pragma unroll
     for (int i = 0; i < kVec; ++i) {
-      const float xhat = (xv[i] - mean[i]) * rstd[i];
-      o[i] = gam[i] * rstd[i] * (g[i] - c1[i] - xhat * c2[i]);
+      ka[i] = gam[i] * rstd[i];
+      kb[i] = -ka[i] * rstd[i] * c2[i];
+      kc[i] = -ka[i] * (c1[i] - mean[i] * rstd[i] * c2[i]);
     }
-    bn_store8<T>(dx + v * kVec, o);
+  }
+  const size_t col = (size_t)cv * kVec;
+  int r = r0 + tyi;
+  for (; r + ty < r1; r += 2 * ty) {                    // 2 rows x 3 streams in flight
+    float g[2][kVec], xv[2][kVec], yv[2][kVec];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const size_t off = (size_t)(r + u * ty) * C + col;
+      bn_load8<T>(dy + off, g[u]);
+      bn_load8<T>(x + off, xv[u]);
+      if (relu) bn_load8<T>(y + off, yv[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const size_t off = (size_t)(r + u * ty) * C + col;
+      float o[kVec];
+#pragma unroll
+      for (int i = 0; i < kVec; ++i) {
+        if (relu && !(yv[u][i] > 0.f)) g[u][i] = 0.f;
+        o[i] = fmaf(ka[i], g[u][i], fmaf(kb[i], xv[u][i], kc[i]));
+      }
+      if (dres != nullptr) bn_store8<T>(dres + off, g[u]);          // gradient of the residual branch = masked dy
+      bn_store8<T>(dx + off, o);
+    }
+  }
+  for (; r < r1; r += ty) {
+    const size_t off = (size_t)r * C + col;
+    float g[kVec], xv[kVec], yv[kVec], o[kVec];
+    bn_load8<T>(dy + off, g);
+    bn_load8<T>(x + off, xv);
+    if (relu) bn_load8<T>(y + off, yv);
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) {
+      if (relu && !(yv[i] > 0.f)) g[i] = 0.f;
+      o[i] = fmaf(ka[i], g[i], fmaf(kb[i], xv[i], kc[i]));
+    }
+    if (dres != nullptr) bn_store8<T>(dres + off, g);
+    bn_store8<T>(dx + off, o);
   }
 }
 
 Tile pick_tile(int R, int C) {
   Tile t;
   const int cv = C / kVec;
-  t.cvb = cv < 32 ? cv : 32;
-  while (kBnThreads % t.cvb != 0) --t.cvb;            // threads along x must divide the block
+  t.cvb = cv < 8 ? cv : 8;                            // <= 64 channels per tile: 128-byte row segments, and the
+  while (kBnThreads % t.cvb != 0) --t.cvb;            //    finishing block has >= 4 lanes per channel
   t.ty = kBnThreads / t.cvb;
   t.grid_x = (cv + t.cvb - 1) / t.cvb;
   // enough row splits to put ~4 blocks on every SM, but keep >= 4 row iterations per block
@@ -305,15 +389,17 @@ Tile pick_tile(int R, int C) {
   int max_by_rows = R / (t.ty * 4);
   if (max_by_rows < 1) max_by_rows = 1;
   t.grid_y = want < max_by_rows ? want : max_by_rows;
-  if (t.grid_y > 1024) t.grid_y = 1024;
+  if (t.grid_y > 256) t.grid_y = 256;
   return t;
 }
 
-int apply_blocks(size_t total_vec) {
-  size_t b = (total_vec + kBnThreads * 4 - 1) / (kBnThreads * 4);
-  if (b > (size_t)kNumSMs * 16) b = (size_t)kNumSMs * 16;
-  if (b < 1) b = 1;
-  return (int)b;
+// apply kernels: same channel tiling, row splits sized so each thread sees >= 4 rows but the grid still fills the GPU
+dim3 apply_grid(const Tile& t, int R) {
+  int want = (8 * kNumSMs + t.grid_x - 1) / t.grid_x;
+  int max_by_rows = R / (t.ty * 4);
+  if (max_by_rows < 1) max_by_rows = 1;
+  int gy = want < max_by_rows ? want : max_by_rows;
+  return dim3(t.grid_x, gy);
 }
 
 }  // namespace
@@ -332,19 +418,18 @@ void launch_bn_forward(const void* x, const void* residual, void* y, DType dt, i
   const Tile t = pick_tile(R, C);
   const size_t smem = (size_t)2 * t.ty * t.cvb * kVec * sizeof(float);
   const dim3 grid(t.grid_x, t.grid_y);
-  const size_t total_vec = (size_t)R * (C / kVec);
   if (dt == DType::BF16) {
     bn_stats_kernel<__nv_bfloat16><<<grid, kBnThreads, smem, s>>>((const __nv_bfloat16*)x, R, C, t.cvb, t.ty, partial, counters, gamma, beta,
                                                                   running_mean, running_var, num_batches, save_mean, save_rstd, scale, shift, eps, momentum);
     B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
-    bn_apply_kernel<__nv_bfloat16><<<apply_blocks(total_vec), kBnThreads, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)residual,
-                                                                                  (__nv_bfloat16*)y, scale, shift, total_vec, C / kVec, relu ? 1 : 0);
+    bn_apply_kernel<__nv_bfloat16><<<apply_grid(t, R), kBnThreads, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)residual,
+                                                                           (__nv_bfloat16*)y, scale, shift, R, C, t.cvb, t.ty, relu ? 1 : 0);
   } else {
     bn_stats_kernel<float><<<grid, kBnThreads, smem, s>>>((const float*)x, R, C, t.cvb, t.ty, partial, counters, gamma, beta, running_mean,
                                                           running_var, num_batches, save_mean, save_rstd, scale, shift, eps, momentum);
     B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
-    bn_apply_kernel<float><<<apply_blocks(total_vec), kBnThreads, 0, s>>>((const float*)x, (const float*)residual, (float*)y, scale, shift,
-                                                                          total_vec, C / kVec, relu ? 1 : 0);
+    bn_apply_kernel<float><<<apply_grid(t, R), kBnThreads, 0, s>>>((const float*)x, (const float*)residual, (float*)y, scale, shift, R, C,
+                                                                   t.cvb, t.ty, relu ? 1 : 0);
   }
   B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
 }
@@ -356,20 +441,19 @@ void launch_bn_backward(const void* dy, const void* x, const void* y, void* dx, 
   const Tile t = pick_tile(R, C);
   const size_t smem = (size_t)2 * t.ty * t.cvb * kVec * sizeof(float);
   const dim3 grid(t.grid_x, t.grid_y);
-  const size_t total_vec = (size_t)R * (C / kVec);
   if (dt == DType::BF16) {
     bn_bwd_reduce_kernel<__nv_bfloat16><<<grid, kBnThreads, smem, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, R, C,
                                                                        t.cvb, t.ty, relu ? 1 : 0, save_mean, save_rstd, partial, counters, dgamma, dbeta, coef);
     B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
-    bn_bwd_apply_kernel<__nv_bfloat16><<<apply_blocks(total_vec), kBnThreads, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,
-                                                                                      (const __nv_bfloat16*)y, (__nv_bfloat16*)dx, (__nv_bfloat16*)dres,
-                                                                                      save_mean, save_rstd, gamma, coef, total_vec, C / kVec, C, relu ? 1 : 0);
+    bn_bwd_apply_kernel<__nv_bfloat16><<<apply_grid(t, R), kBnThreads, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,
+                                                                               (const __nv_bfloat16*)y, (__nv_bfloat16*)dx, (__nv_bfloat16*)dres,
+                                                                               save_mean, save_rstd, gamma, coef, R, C, t.cvb, t.ty, relu ? 1 : 0);
   } else {
     bn_bwd_reduce_kernel<float><<<grid, kBnThreads, smem, s>>>((const float*)dy, (const float*)x, (const float*)y, R, C, t.cvb, t.ty, relu ? 1 : 0,
                                                                save_mean, save_rstd, partial, counters, dgamma, dbeta, coef);
     B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
-    bn_bwd_apply_kernel<float><<<apply_blocks(total_vec), kBnThreads, 0, s>>>((const float*)dy, (const float*)x, (const float*)y, (float*)dx,
-                                                                              (float*)dres, save_mean, save_rstd, gamma, coef, total_vec, C / kVec, C, relu ? 1 : 0);
+    bn_bwd_apply_kernel<float><<<apply_grid(t, R), kBnThreads, 0, s>>>((const float*)dy, (const float*)x, (const float*)y, (float*)dx,
+                                                                       (float*)dres, save_mean, save_rstd, gamma, coef, R, C, t.cvb, t.ty, relu ? 1 : 0);
   }
   B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
 }

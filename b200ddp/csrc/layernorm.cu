@@ -154,31 +154,21 @@ __global__ void __launch_bounds__(kLnThreads) layernorm_fwd_fast_kernel(const T*
   }
 }
 
+// dx only: rows live in registers, no cross-row state -> light enough for 2 CTAs per SM.
 template <typename T>
-__global__ void __launch_bounds__(kLnThreads) layernorm_bwd_fast_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ gamma,
-                                                                        const float* __restrict__ mean, const float* __restrict__ rstd, int rows,
-                                                                        int cols, T* __restrict__ dx, float* __restrict__ dgamma_partial,
-                                                                        float* __restrict__ dbeta_partial) {
-  extern __shared__ float smem[];            // [2][cols] per-CTA column accumulators
-  float* sg = smem;
-  float* sb = smem + cols;
-  for (int i = threadIdx.x; i < 2 * cols; i += blockDim.x) smem[i] = 0.f;
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+__global__ void __launch_bounds__(kLnThreads, 2) layernorm_bwd_dx_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ gamma,
+                                                                         const float* __restrict__ mean, const float* __restrict__ rstd, int rows,
+                                                                         int cols, T* __restrict__ dx) {
+  const int lane = threadIdx.x & 31, warps = blockDim.x >> 5;
   const int nchunk = cols >> 3;
-  float g[kLnChunks][8], ag[kLnChunks][8], ab[kLnChunks][8];
+  float g[kLnChunks][8];
 #pragma unroll
   for (int c = 0; c < kLnChunks; ++c) {
     const int ch = lane + 32 * c;
     if (ch < nchunk) ln_load8<T>(gamma + 8 * ch, g[c]);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { ag[c][j] = 0.f; ab[c][j] = 0.f; }
   }
   const float inv = 1.f / (float)cols;
-  const int rows_per_cta = (rows + gridDim.x - 1) / gridDim.x;
-  const int r0 = blockIdx.x * rows_per_cta;
-  const int r1 = min(rows, r0 + rows_per_cta);
-  for (int row = r0 + warp; row < r1; row += warps) {
+  for (int row = blockIdx.x * warps + (threadIdx.x >> 5); row < rows; row += gridDim.x * warps) {
     const T* xr = x + (size_t)row * cols;
     const T* dyr = dy + (size_t)row * cols;
     const float mu = mean[row], rs = rstd[row];
@@ -193,11 +183,9 @@ __global__ void __launch_bounds__(kLnThreads) layernorm_bwd_fast_kernel(const T*
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           xn[c][j] = (xn[c][j] - mu) * rs;
-          const float dg = d[c][j] * g[c][j];
-          s1 += dg;
-          s2 += dg * xn[c][j];
-          ag[c][j] += d[c][j] * xn[c][j];
-          ab[c][j] += d[c][j];
+          d[c][j] *= g[c][j];
+          s1 += d[c][j];
+          s2 = fmaf(d[c][j], xn[c][j], s2);
         }
       }
     }
@@ -210,25 +198,87 @@ __global__ void __launch_bounds__(kLnThreads) layernorm_bwd_fast_kernel(const T*
       if (ch < nchunk) {
         float o[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = rs * (d[c][j] * g[c][j] - s1 - xn[c][j] * s2);
+        for (int j = 0; j < 8; ++j) o[j] = rs * (d[c][j] - s1 - xn[c][j] * s2);
         ln_store8<T>(dxr + 8 * ch, o);
       }
     }
   }
-  // one shared-memory reduction per warp per column at the very end
+}
+
+// dgamma / dbeta: column reduction over rows (same scheme as the BatchNorm reductions): threads own 8 columns,
+// rows are strided over the block and over gridDim.y splits, the last block of a column tile sums the partials
+// in a fixed order.  Re-reads dy and x, which are L2-resident right after the dx kernel.
+template <typename T>
+__global__ void __launch_bounds__(kLnThreads) layernorm_param_grad_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                                          const float* __restrict__ mean, const float* __restrict__ rstd, int rows,
+                                                                          int cols, int cvb, int ty, float* __restrict__ partial,
+                                                                          unsigned int* __restrict__ counters, T* __restrict__ dgamma,
+                                                                          T* __restrict__ dbeta) {
+  extern __shared__ float smem[];
+  __shared__ bool is_last;
+  const int tx = threadIdx.x % cvb, tyi = threadIdx.x / cvb;
+  const int cv = blockIdx.x * cvb + tx;
+  const int S = gridDim.y;
+  const int rows_per = (rows + S - 1) / S;
+  const int r0 = blockIdx.y * rows_per, r1 = min(rows, r0 + rows_per);
+  float ag[8], ab[8];
 #pragma unroll
-  for (int c = 0; c < kLnChunks; ++c) {
-    const int ch = lane + 32 * c;
-    if (ch < nchunk) {
+  for (int i = 0; i < 8; ++i) { ag[i] = 0.f; ab[i] = 0.f; }
+  if (cv * 8 < cols) {
+    const size_t col = (size_t)cv * 8;
+    int r = r0 + tyi;
+    for (; r + ty < r1; r += 2 * ty) {
+      float d0[8], x0[8], d1[8], x1[8];
+      ln_load8<T>(dy + (size_t)r * cols + col, d0);
+      ln_load8<T>(x + (size_t)r * cols + col, x0);
+      ln_load8<T>(dy + (size_t)(r + ty) * cols + col, d1);
+      ln_load8<T>(x + (size_t)(r + ty) * cols + col, x1);
+      const float m0 = mean[r], s0 = rstd[r], m1 = mean[r + ty], s1 = rstd[r + ty];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { atomicAdd(&sg[8 * ch + j], ag[c][j]); atomicAdd(&sb[8 * ch + j], ab[c][j]); }
+      for (int i = 0; i < 8; ++i) {
+        ab[i] += d0[i] + d1[i];
+        ag[i] = fmaf(d0[i], (x0[i] - m0) * s0, ag[i]);
+        ag[i] = fmaf(d1[i], (x1[i] - m1) * s1, ag[i]);
+      }
+    }
+    for (; r < r1; r += ty) {
+      float d0[8], x0[8];
+      ln_load8<T>(dy + (size_t)r * cols + col, d0);
+      ln_load8<T>(x + (size_t)r * cols + col, x0);
+      const float m0 = mean[r], s0 = rstd[r];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { ab[i] += d0[i]; ag[i] = fmaf(d0[i], (x0[i] - m0) * s0, ag[i]); }
     }
   }
+  const int width = cvb * 8;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { smem[(0 * ty + tyi) * width + tx * 8 + i] = ag[i]; smem[(1 * ty + tyi) * width + tx * 8 + i] = ab[i]; }
   __syncthreads();
-  for (int i = threadIdx.x; i < cols; i += blockDim.x) {
-    dgamma_partial[(size_t)blockIdx.x * cols + i] = sg[i];
-    dbeta_partial[(size_t)blockIdx.x * cols + i] = sb[i];
+  for (int idx = threadIdx.x; idx < 2 * width; idx += blockDim.x) {
+    const int a = idx / width, c = idx % width;
+    float sum = 0.f;
+    for (int rr = 0; rr < ty; ++rr) sum += smem[(a * ty + rr) * width + c];
+    const int ch = blockIdx.x * width + c;
+    if (ch < cols) partial[(size_t)(a * S + blockIdx.y) * cols + ch] = sum;
   }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int ticket = atomicAdd(&counters[blockIdx.x], 1u);
+    is_last = (ticket == (unsigned int)S - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  for (int c = threadIdx.x; c < width; c += blockDim.x) {
+    const int ch = blockIdx.x * width + c;
+    if (ch >= cols) continue;
+    float sg = 0.f, sb = 0.f;
+    for (int k = 0; k < S; ++k) { sg += __ldcg(&partial[(size_t)(0 * S + k) * cols + ch]); sb += __ldcg(&partial[(size_t)(1 * S + k) * cols + ch]); }
+    dgamma[ch] = from_f32<T>(sg);
+    dbeta[ch] = from_f32<T>(sb);
+  }
+  if (threadIdx.x == 0) counters[blockIdx.x] = 0u;
 }
 
 template <typename T>
@@ -281,17 +331,34 @@ void launch_layernorm_bwd(const void* dy, const void* x, const void* gamma, cons
   const bool fast = (cols % 8 == 0) && cols <= 8 * 32 * kLnChunks &&
                     ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx) |
                       reinterpret_cast<uintptr_t>(gamma)) & 31u) == 0;
-  if (fast && dt == DType::BF16) {
-    layernorm_bwd_fast_kernel<__nv_bfloat16><<<partial_rows, kLnThreads, smem, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,
-                                                                                  (const __nv_bfloat16*)gamma, mean, rstd, rows, cols,
-                                                                                  (__nv_bfloat16*)dx, dgamma_partial, dbeta_partial);
-    layernorm_bwd_finish_kernel<__nv_bfloat16><<<(cols + 255) / 256, 256, 0, s>>>(dgamma_partial, dbeta_partial, partial_rows, cols,
-                                                                                (__nv_bfloat16*)dgamma, (__nv_bfloat16*)dbeta);
-  } else if (fast) {
-    layernorm_bwd_fast_kernel<float><<<partial_rows, kLnThreads, smem, s>>>((const float*)dy, (const float*)x, (const float*)gamma, mean, rstd,
-                                                                          rows, cols, (float*)dx, dgamma_partial, dbeta_partial);
-    layernorm_bwd_finish_kernel<float><<<(cols + 255) / 256, 256, 0, s>>>(dgamma_partial, dbeta_partial, partial_rows, cols,
-                                                                        (float*)dgamma, (float*)dbeta);
+  if (fast) {
+    // workspace carved from the caller's partial buffers: dgamma_partial = [2][S][cols] partial sums, dbeta_partial = counters
+    const int cv = cols / 8;
+    int cvb = cv < 32 ? cv : 32;
+    while (kLnThreads % cvb != 0) --cvb;
+    const int ty = kLnThreads / cvb;
+    const int gx = (cv + cvb - 1) / cvb;
+    int gy = (4 * kNumSMs + gx - 1) / gx;
+    const int by_rows = rows / (ty * 4) < 1 ? 1 : rows / (ty * 4);
+    if (gy > by_rows) gy = by_rows;
+    if (gy > partial_rows / 2) gy = partial_rows / 2 < 1 ? 1 : partial_rows / 2;     // capacity of the partial buffer
+    int blocks = (rows + 7) / 8;
+    if (blocks > 16 * kNumSMs) blocks = 16 * kNumSMs;
+    const size_t psmem = (size_t)2 * kLnThreads * 8 * sizeof(float);
+    unsigned int* counters = reinterpret_cast<unsigned int*>(dbeta_partial);
+    B200_CUDA_CHECK(cudaMemsetAsync(counters, 0, sizeof(unsigned int) * gx, s));   // fresh scratch from the caller
+    if (dt == DType::BF16) {
+      layernorm_bwd_dx_kernel<__nv_bfloat16><<<blocks, kLnThreads, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)gamma,
+                                                                           mean, rstd, rows, cols, (__nv_bfloat16*)dx);
+      layernorm_param_grad_kernel<__nv_bfloat16><<<dim3(gx, gy), kLnThreads, psmem, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd,
+                                                                                         rows, cols, cvb, ty, dgamma_partial, counters,
+                                                                                         (__nv_bfloat16*)dgamma, (__nv_bfloat16*)dbeta);
+    } else {
+      layernorm_bwd_dx_kernel<float><<<blocks, kLnThreads, 0, s>>>((const float*)dy, (const float*)x, (const float*)gamma, mean, rstd, rows, cols,
+                                                                   (float*)dx);
+      layernorm_param_grad_kernel<float><<<dim3(gx, gy), kLnThreads, psmem, s>>>((const float*)dy, (const float*)x, mean, rstd, rows, cols, cvb, ty,
+                                                                                 dgamma_partial, counters, (float*)dgamma, (float*)dbeta);
+    }
   } else if (dt == DType::BF16) {
     layernorm_bwd_kernel<__nv_bfloat16><<<partial_rows, kLnThreads, smem, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,
                                                                              (const __nv_bfloat16*)gamma, mean, rstd, rows, cols,

@@ -13,11 +13,37 @@ Here:
 """
 from __future__ import annotations
 
+import atexit
 import queue
 import threading
 from typing import Iterator, List, Optional, Sequence, Tuple
 
 import torch
+
+
+_ACTIVE = []          # (stop event, queue, thread) of running loader helper threads
+_ACTIVE_LOCK = threading.Lock()
+
+
+def _stop_helper(entry) -> None:
+    stop, q, t = entry
+    stop.set()
+    try:
+        while True:
+            q.get_nowait()
+    except queue.Empty:
+        pass
+    t.join(timeout=2.0)
+
+
+@atexit.register
+def _shutdown_loader_threads() -> None:
+    """A helper thread left inside native code at interpreter teardown aborts the process; stop them first."""
+    with _ACTIVE_LOCK:
+        entries = list(_ACTIVE)
+        _ACTIVE.clear()
+    for e in entries:
+        _stop_helper(e)
 
 
 class PinnedBatch(tuple):
@@ -80,6 +106,9 @@ class BatchLoader:
 
         t = threading.Thread(target=work, name="b200ddp-batch-loader", daemon=True)
         t.start()
+        entry = (stop, q, t)
+        with _ACTIVE_LOCK:
+            _ACTIVE.append(entry)
         try:
             while True:
                 item = q.get()
@@ -89,13 +118,10 @@ class BatchLoader:
                     raise item
                 yield item
         finally:
-            stop.set()
-            try:                      # unblock a producer waiting on a full queue, then wait for it to leave native code
-                while True:
-                    q.get_nowait()
-            except queue.Empty:
-                pass
-            t.join(timeout=2.0)
+            with _ACTIVE_LOCK:
+                if entry in _ACTIVE:
+                    _ACTIVE.remove(entry)
+            _stop_helper(entry)       # unblock a producer waiting on a full queue, wait for it to leave native code
 
     def _produce(self) -> Iterator[Tuple[torch.Tensor, ...]]:
         indices: List[int] = []

@@ -10,7 +10,7 @@ echo "== bench"; timeout 600 python bench.py --gpus 1 --steps 40 --warmup 8 > $O
 echo "== kernel bench"; timeout 900 python bench/kernel_bench.py --out $O/kernels.json > $O/kernels.log 2>&1; echo "kernel bench rc=$?"
 cat $O/kernels.log
 echo "== launch list of one bench step (CUDA graph replay)"
-timeout 600 $NCU --metrics gpu__time_duration.sum --profile-from-start off --csv --log-file $O/launches_graph.csv \
+timeout 600 $NCU --cache-control none --metrics gpu__time_duration.sum --profile-from-start off --csv --log-file $O/launches_graph.csv \
     python bench.py --steps 2 --warmup 6 --skip_e2e --profile_range > $O/launches_graph_bench.json 2> $O/launches_graph.err; echo "graph launch list rc=$?"
 if [ "$MODE" = "full" ]; then
 echo "== ncu full: tcgen05 GEMM (2-CTA)"
