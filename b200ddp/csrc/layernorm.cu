@@ -297,7 +297,7 @@ __global__ void layernorm_bwd_finish_kernel(const float* __restrict__ dgamma_par
 int layernorm_partial_rows(int rows) {
   int p = (rows + 63) / 64;
   if (p > 2 * kNumSMs) p = 2 * kNumSMs;
-  if (p < 1) p = 1;
+  if (p < 2) p = 2;          // the column-reduce path stores [2][splits][cols] partials in this buffer
   return p;
 }
 

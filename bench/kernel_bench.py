@@ -53,7 +53,7 @@ def timeit(fn, iters=20, flush=True):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", type=str, default="gemm,bn,sgd,ln,xent,mse,input")
+    ap.add_argument("--only", type=str, default="gemm,bn,sgd,ln,xent,mse,input,h2d")
     ap.add_argument("--out", type=str, default=None)
     ap.add_argument("--iters", type=int, default=20)
     args = ap.parse_args()
@@ -200,6 +200,16 @@ def main():
         ms = timeit(lambda: C.normalize_to_channels_last(x, dst, mean, istd, 1.0), args.iters)
         lib = timeit(lambda: x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last), args.iters)
         record("normalize+cast+NHWC 256x3x224x224", ms, bytes_=x.numel() * 6, lib_ms=lib)
+
+    if "h2d" in want:
+        for nbytes, label in ((32 * 3 * 224 * 224 * 4, "fp32 batch 19.3 MB"), (32 * 3 * 224 * 224, "uint8 batch 4.8 MB"), (256 << 20, "256 MB")):
+            host = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+            devb = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            ms = timeit(lambda: devb.copy_(host, non_blocking=True), args.iters, flush=False)
+            rows.append({"kernel": f"H2D pinned {label}", "ms": ms, "gbs": nbytes / ms / 1e6})
+            print(f"H2D pinned {label:32s} {ms:8.3f} ms {nbytes / ms / 1e6:8.1f} GB/s", flush=True)
+            ms = timeit(lambda: host.copy_(devb, non_blocking=True), args.iters, flush=False)
+            print(f"D2H pinned {label:32s} {ms:8.3f} ms {nbytes / ms / 1e6:8.1f} GB/s", flush=True)
 
     if args.out:
         os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
