@@ -9,7 +9,8 @@
 //   forward : bn_stats      column sum / sum-of-squares -> mean, rstd, scale = gamma*rstd, shift = beta - mean*scale,
 //                           running statistics and num_batches_tracked updated by the last block (deterministic)
 //             bn_apply      y = relu(x*scale + shift + residual)            one pass, 16-byte accesses
-//   backward: bn_bwd_reduce sum(dy*), sum(dy* * xhat) with the ReLU mask recomputed from y; dgamma/dbeta
+//   backward: bn_bwd_reduce sum(dy*), sum(dy* * xhat); the ReLU mask is a 1-bit/element bitmap written by bn_apply
+//                           (1/16 of re-reading y in bf16, twice); dgamma/dbeta
 //             bn_bwd_apply  dx = scale*(dy* - mean(dy*) - xhat*mean(dy* xhat)), and the residual branch's grad
 //
 // Threads own 8 consecutive channels (one 16-byte vector of bf16); rows are strided across the block and
@@ -164,8 +165,8 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const T* __restric
 
 template <typename T>
 __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ residual, T* __restrict__ y,
-                                                             const float* __restrict__ scale, const float* __restrict__ shift, int R, int C,
-                                                             int cvb, int ty, int relu) {
+                                                             unsigned char* __restrict__ mask, const float* __restrict__ scale,
+                                                             const float* __restrict__ shift, int R, int C, int cvb, int ty, int relu) {
   const int tx = threadIdx.x % cvb, tyi = threadIdx.x / cvb;
   const int cv = blockIdx.x * cvb + tx;
   if (cv * kVec >= C) return;
@@ -187,12 +188,16 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const T* __restric
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
 #pragma unroll
+      unsigned int bits = 0;
+#pragma unroll
       for (int i = 0; i < kVec; ++i) {
         float v = fmaf(f[u][i], sc[i], sh[i]);
         if (residual != nullptr) v += rs[u][i];
+        bits |= (v > 0.f ? 1u : 0u) << i;
         f[u][i] = relu ? fmaxf(v, 0.f) : v;
       }
       bn_store8<T>(y + (size_t)(r + u * ty) * C + col, f[u]);
+      if (mask != nullptr) mask[(size_t)(r + u * ty) * (C / kVec) + cv] = (unsigned char)bits;
     }
   }
   for (; r < r1; r += ty) {
@@ -200,18 +205,22 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const T* __restric
     bn_load8<T>(x + (size_t)r * C + col, f);
     if (residual != nullptr) bn_load8<T>(residual + (size_t)r * C + col, rs);
 #pragma unroll
+    unsigned int bits = 0;
+#pragma unroll
     for (int i = 0; i < kVec; ++i) {
       float v = fmaf(f[i], sc[i], sh[i]);
       if (residual != nullptr) v += rs[i];
+      bits |= (v > 0.f ? 1u : 0u) << i;
       f[i] = relu ? fmaxf(v, 0.f) : v;
     }
     bn_store8<T>(y + (size_t)r * C + col, f);
+    if (mask != nullptr) mask[(size_t)r * (C / kVec) + cv] = (unsigned char)bits;
   }
 }
 
 // ------------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y,
+__global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const unsigned char* __restrict__ y,
                                                                   int R, int C, int cvb, int ty, int relu, const float* __restrict__ save_mean,
                                                                   const float* __restrict__ save_rstd, float* __restrict__ partial,
                                                                   unsigned int* __restrict__ counters, float* __restrict__ dgamma,
@@ -233,32 +242,33 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(const T* __re
     const size_t col = (size_t)cv * kVec;
     int r = r0 + tyi;
     for (; r + ty < r1; r += 2 * ty) {                  // 2 rows x 3 streams = 6 independent 16-byte loads in flight
-      float g[2][kVec], xv[2][kVec], yv[2][kVec];
+      float g[2][kVec], xv[2][kVec];
+      unsigned int mk[2] = {0xffu, 0xffu};
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const size_t off = (size_t)(r + u * ty) * C + col;
         bn_load8<T>(dy + off, g[u]);
         bn_load8<T>(x + off, xv[u]);
-        if (relu) bn_load8<T>(y + off, yv[u]);
+        if (relu) mk[u] = y[(size_t)(r + u * ty) * (C / kVec) + cv];
       }
 #pragma unroll
       for (int u = 0; u < 2; ++u)
 #pragma unroll
         for (int i = 0; i < kVec; ++i) {
-          const float gm = (relu && !(yv[u][i] > 0.f)) ? 0.f : g[u][i];
+          const float gm = ((mk[u] >> i) & 1u) ? g[u][i] : 0.f;
           acc[0][i] += gm;
           acc[1][i] = fmaf(gm, (xv[u][i] - mean[i]) * rstd[i], acc[1][i]);
         }
     }
     for (; r < r1; r += ty) {
-      float g[kVec], xv[kVec], yv[kVec];
+      float g[kVec], xv[kVec];
       const size_t off = (size_t)r * C + col;
       bn_load8<T>(dy + off, g);
       bn_load8<T>(x + off, xv);
-      if (relu) bn_load8<T>(y + off, yv);
+      const unsigned int mk = relu ? y[(size_t)r * (C / kVec) + cv] : 0xffu;
 #pragma unroll
       for (int i = 0; i < kVec; ++i) {
-        const float gm = (relu && !(yv[i] > 0.f)) ? 0.f : g[i];
+        const float gm = ((mk >> i) & 1u) ? g[i] : 0.f;
         acc[0][i] += gm;
         acc[1][i] = fmaf(gm, (xv[i] - mean[i]) * rstd[i], acc[1][i]);
       }
@@ -311,7 +321,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(const T* __re
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y,
+__global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const unsigned char* __restrict__ y,
                                                                  T* __restrict__ dx, T* __restrict__ dres, const float* __restrict__ save_mean,
                                                                  const float* __restrict__ save_rstd, const float* __restrict__ gamma,
                                                                  const float* __restrict__ coef, int R, int C, int cvb, int ty, int relu) {
@@ -340,13 +350,14 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const T* __res
   const size_t col = (size_t)cv * kVec;
   int r = r0 + tyi;
   for (; r + ty < r1; r += 2 * ty) {                    // 2 rows x 3 streams in flight
-    float g[2][kVec], xv[2][kVec], yv[2][kVec];
+    float g[2][kVec], xv[2][kVec];
+    unsigned int mk[2] = {0xffu, 0xffu};
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const size_t off = (size_t)(r + u * ty) * C + col;
       bn_load8<T>(dy + off, g[u]);
       bn_load8<T>(x + off, xv[u]);
-      if (relu) bn_load8<T>(y + off, yv[u]);
+      if (relu) mk[u] = y[(size_t)(r + u * ty) * (C / kVec) + cv];
     }
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
@@ -354,7 +365,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const T* __res
       float o[kVec];
 #pragma unroll
       for (int i = 0; i < kVec; ++i) {
-        if (relu && !(yv[u][i] > 0.f)) g[u][i] = 0.f;
+        if (!((mk[u] >> i) & 1u)) g[u][i] = 0.f;
         o[i] = fmaf(ka[i], g[u][i], fmaf(kb[i], xv[u][i], kc[i]));
       }
       if (dres != nullptr) bn_store8<T>(dres + off, g[u]);          // gradient of the residual branch = masked dy
@@ -363,13 +374,13 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const T* __res
   }
   for (; r < r1; r += ty) {
     const size_t off = (size_t)r * C + col;
-    float g[kVec], xv[kVec], yv[kVec], o[kVec];
+    float g[kVec], xv[kVec], o[kVec];
     bn_load8<T>(dy + off, g);
     bn_load8<T>(x + off, xv);
-    if (relu) bn_load8<T>(y + off, yv);
+    const unsigned int mk = relu ? y[(size_t)r * (C / kVec) + cv] : 0xffu;
 #pragma unroll
     for (int i = 0; i < kVec; ++i) {
-      if (relu && !(yv[i] > 0.f)) g[i] = 0.f;
+      if (!((mk >> i) & 1u)) g[i] = 0.f;
       o[i] = fmaf(ka[i], g[i], fmaf(kb[i], xv[i], kc[i]));
     }
     if (dres != nullptr) bn_store8<T>(dres + off, g);
@@ -410,7 +421,7 @@ void bn_workspace_sizes(int R, int C, size_t* partial_floats, size_t* counters) 
   *counters = (size_t)t.grid_x;
 }
 
-void launch_bn_forward(const void* x, const void* residual, void* y, DType dt, int R, int C, const float* gamma, const float* beta,
+void launch_bn_forward(const void* x, const void* residual, void* y, unsigned char* mask, DType dt, int R, int C, const float* gamma, const float* beta,
                        float* running_mean, float* running_var, long long* num_batches, float* save_mean, float* save_rstd,
                        float* scale, float* shift, float* partial, unsigned int* counters, float eps, float momentum, bool relu,
                        cudaStream_t s) {
@@ -423,12 +434,12 @@ void launch_bn_forward(const void* x, const void* residual, void* y, DType dt, i
                                                                   running_mean, running_var, num_batches, save_mean, save_rstd, scale, shift, eps, momentum);
     B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
     bn_apply_kernel<__nv_bfloat16><<<apply_grid(t, R), kBnThreads, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)residual,
-                                                                           (__nv_bfloat16*)y, scale, shift, R, C, t.cvb, t.ty, relu ? 1 : 0);
+                                                                           (__nv_bfloat16*)y, mask, scale, shift, R, C, t.cvb, t.ty, relu ? 1 : 0);
   } else {
     bn_stats_kernel<float><<<grid, kBnThreads, smem, s>>>((const float*)x, R, C, t.cvb, t.ty, partial, counters, gamma, beta, running_mean,
                                                           running_var, num_batches, save_mean, save_rstd, scale, shift, eps, momentum);
     B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
-    bn_apply_kernel<float><<<apply_grid(t, R), kBnThreads, 0, s>>>((const float*)x, (const float*)residual, (float*)y, scale, shift, R, C,
+    bn_apply_kernel<float><<<apply_grid(t, R), kBnThreads, 0, s>>>((const float*)x, (const float*)residual, (float*)y, mask, scale, shift, R, C,
                                                                    t.cvb, t.ty, relu ? 1 : 0);
   }
   B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
@@ -442,17 +453,17 @@ void launch_bn_backward(const void* dy, const void* x, const void* y, void* dx, 
   const size_t smem = (size_t)2 * t.ty * t.cvb * kVec * sizeof(float);
   const dim3 grid(t.grid_x, t.grid_y);
   if (dt == DType::BF16) {
-    bn_bwd_reduce_kernel<__nv_bfloat16><<<grid, kBnThreads, smem, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, R, C,
+    bn_bwd_reduce_kernel<__nv_bfloat16><<<grid, kBnThreads, smem, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const unsigned char*)y, R, C,
                                                                        t.cvb, t.ty, relu ? 1 : 0, save_mean, save_rstd, partial, counters, dgamma, dbeta, coef);
     B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
     bn_bwd_apply_kernel<__nv_bfloat16><<<apply_grid(t, R), kBnThreads, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,
-                                                                               (const __nv_bfloat16*)y, (__nv_bfloat16*)dx, (__nv_bfloat16*)dres,
+                                                                               (const unsigned char*)y, (__nv_bfloat16*)dx, (__nv_bfloat16*)dres,
                                                                                save_mean, save_rstd, gamma, coef, R, C, t.cvb, t.ty, relu ? 1 : 0);
   } else {
-    bn_bwd_reduce_kernel<float><<<grid, kBnThreads, smem, s>>>((const float*)dy, (const float*)x, (const float*)y, R, C, t.cvb, t.ty, relu ? 1 : 0,
+    bn_bwd_reduce_kernel<float><<<grid, kBnThreads, smem, s>>>((const float*)dy, (const float*)x, (const unsigned char*)y, R, C, t.cvb, t.ty, relu ? 1 : 0,
                                                                save_mean, save_rstd, partial, counters, dgamma, dbeta, coef);
     B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
-    bn_bwd_apply_kernel<float><<<apply_grid(t, R), kBnThreads, 0, s>>>((const float*)dy, (const float*)x, (const float*)y, (float*)dx,
+    bn_bwd_apply_kernel<float><<<apply_grid(t, R), kBnThreads, 0, s>>>((const float*)dy, (const float*)x, (const unsigned char*)y, (float*)dx,
                                                                        (float*)dres, save_mean, save_rstd, gamma, coef, R, C, t.cvb, t.ty, relu ? 1 : 0);
   }
   B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);

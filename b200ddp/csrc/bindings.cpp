@@ -460,12 +460,13 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       res = residual->data_ptr();
     }
     float* st = stats.data_ptr<float>();
-    launch_bn_forward(x.data_ptr(), res, y.data_ptr(), dtype_of(x), R, C, gamma.data_ptr<float>(), beta.data_ptr<float>(),
+    at::Tensor mask = relu ? at::empty({(int64_t)R, (int64_t)(C / 8)}, x.options().dtype(at::kByte)) : at::Tensor();
+    launch_bn_forward(x.data_ptr(), res, y.data_ptr(), relu ? mask.data_ptr<uint8_t>() : nullptr, dtype_of(x), R, C, gamma.data_ptr<float>(), beta.data_ptr<float>(),
                       running_mean.has_value() ? running_mean->data_ptr<float>() : nullptr,
                       running_var.has_value() ? running_var->data_ptr<float>() : nullptr,
                       num_batches.has_value() ? (long long*)num_batches->data_ptr<int64_t>() : nullptr, st, st + C, st + 2 * C, st + 3 * C,
                       partial.data_ptr<float>(), (unsigned int*)counters.data_ptr<int>(), (float)eps, (float)momentum, relu, cur_stream());
-    return std::make_tuple(y, stats);
+    return std::make_tuple(y, stats, mask);
   });
   m.def("bn_backward", [](at::Tensor dy, at::Tensor x, c10::optional<at::Tensor> y, at::Tensor gamma, at::Tensor stats, bool relu,
                           bool need_dres, at::Tensor partial, at::Tensor counters) {
@@ -480,7 +481,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     at::Tensor dparams = at::empty({4, C}, fopt);   // rows: dgamma, dbeta, coef1, coef2
     float* dp = dparams.data_ptr<float>();
     const float* st = stats.data_ptr<float>();
-    TORCH_CHECK(!relu || y.has_value(), "bn_backward: the ReLU mask needs the saved output");
+    TORCH_CHECK(!relu || (y.has_value() && y->scalar_type() == at::kByte), "bn_backward: needs the ReLU bitmask written by bn_forward");
     launch_bn_backward(dyc.data_ptr(), x.data_ptr(), relu ? y->data_ptr() : nullptr, dx.data_ptr(), need_dres ? dres.data_ptr() : nullptr,
                        dtype_of(x), R, C, gamma.data_ptr<float>(), st, st + C, dp, dp + C, dp + 2 * C, partial.data_ptr<float>(),
                        (unsigned int*)counters.data_ptr<int>(), relu, cur_stream());

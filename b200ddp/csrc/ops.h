@@ -67,11 +67,11 @@ void launch_small_linear_bwd(const float* dy, const float* x, const float* w, co
 // ---------------- fused training BatchNorm (+residual) (+ReLU), channels_last (batchnorm.cu) --------------
 // x viewed as row-major [R = N*H*W, C]; C % 8 == 0; gamma/beta/statistics fp32.
 void bn_workspace_sizes(int R, int C, size_t* partial_floats, size_t* counters);
-void launch_bn_forward(const void* x, const void* residual, void* y, DType dt, int R, int C, const float* gamma, const float* beta,
+void launch_bn_forward(const void* x, const void* residual, void* y, unsigned char* relu_mask /*[R, C/8] or null*/, DType dt, int R, int C, const float* gamma, const float* beta,
                        float* running_mean, float* running_var, long long* num_batches, float* save_mean, float* save_rstd,
                        float* scale, float* shift, float* partial, unsigned int* counters, float eps, float momentum, bool relu,
                        cudaStream_t s);
-void launch_bn_backward(const void* dy, const void* x, const void* y, void* dx, void* dres, DType dt, int R, int C, const float* gamma,
+void launch_bn_backward(const void* dy, const void* x, const void* relu_mask, void* dx, void* dres, DType dt, int R, int C, const float* gamma,
                         const float* save_mean, const float* save_rstd, float* dgamma, float* dbeta, float* coef, float* partial,
                         unsigned int* counters, bool relu, cudaStream_t s);
 

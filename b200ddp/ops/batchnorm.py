@@ -19,9 +19,10 @@ class _FusedBN(torch.autograd.Function):
     def forward(ctx, x, residual, weight, bias, module, relu):
         C = _ext.get()
         ws = module._workspace(x)
-        y, stats = C.bn_forward(x, residual, weight, bias, module.running_mean, module.running_var, module.num_batches_tracked,
-                                module.eps, module.momentum if module.momentum is not None else 0.1, relu, ws[0], ws[1])
-        ctx.save_for_backward(x, y if relu else None, weight, stats)
+        y, stats, mask = C.bn_forward(x, residual, weight, bias, module.running_mean, module.running_var,
+                                      module.num_batches_tracked, module.eps,
+                                      module.momentum if module.momentum is not None else 0.1, relu, ws[0], ws[1])
+        ctx.save_for_backward(x, mask if relu else None, weight, stats)    # 1 bit / element instead of keeping y for the mask
         ctx.relu = relu
         ctx.has_residual = residual is not None
         ctx.module = module

@@ -125,9 +125,9 @@ def main():
             ms = timeit(fwd, args.iters)
             lib = timeit(lambda: torch.relu(ref(x) + res), args.iters)
             record(f"bn+add+relu fwd {shape}", ms, bytes_=nbytes * 4, lib_ms=lib, note="min traffic: x read twice (2nd from L2), res, y")
-            y, stats = fwd()
+            y, stats, mask = fwd()
             dy = torch.randn_like(x)
-            ms = timeit(lambda: C.bn_backward(dy, x, y, bn.weight, stats, True, True, ws[2], ws[3]), args.iters)
+            ms = timeit(lambda: C.bn_backward(dy, x, mask, bn.weight, stats, True, True, ws[2], ws[3]), args.iters)
             xr = x.clone().requires_grad_()
             rr = res.clone().requires_grad_()
             yl = torch.relu(ref(xr) + rr)
