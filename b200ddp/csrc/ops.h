@@ -75,6 +75,10 @@ void launch_bn_backward(const void* dy, const void* x, const void* relu_mask, vo
                         const float* save_mean, const float* save_rstd, float* dgamma, float* dbeta, float* coef, float* partial,
                         unsigned int* counters, bool relu, cudaStream_t s);
 
+// ---------------- 3x3/s2/p1 max pooling, channels_last (pool.cu) ------------------------------------------
+void launch_maxpool3x3s2_fwd(const void* x, void* y, unsigned char* idx, DType dt, int N, int H, int W, int C, cudaStream_t s);
+void launch_maxpool3x3s2_bwd(const void* dy, const unsigned char* idx, void* dx, DType dt, int N, int H, int W, int C, cudaStream_t s);
+
 // ---------------- input pipeline (input.cu) -----------------------------------------------------
 // NCHW (u8 or fp32) -> NHWC-in-memory (channels_last) bf16/fp32 with per-channel (x*scale - mean)/std
 void launch_normalize_to_channels_last(const void* src, DType src_dt, void* dst, DType dst_dt, int n, int c, int h,

@@ -26,14 +26,7 @@ _ACTIVE_LOCK = threading.Lock()
 
 
 def _stop_helper(entry) -> None:
-    stop, q, t = entry
-    stop.set()
-    try:
-        while True:
-            q.get_nowait()
-    except queue.Empty:
-        pass
-    t.join(timeout=2.0)
+    entry.stop()
 
 
 @atexit.register
@@ -53,7 +46,7 @@ class PinnedBatch(tuple):
 
 class BatchLoader:
     def __init__(self, dataset, batch_size: int, sampler=None, drop_last: bool = False, pin_memory: bool = True,
-                 num_slots: int = 6, background: bool = True):
+                 num_slots: int = 8, background: bool = True, workers: int = 3):
         self.dataset = dataset
         self.batch_size = int(batch_size)
         self.sampler = sampler if sampler is not None else torch.utils.data.SequentialSampler(dataset)
@@ -66,6 +59,7 @@ class BatchLoader:
         # gather batches on a helper thread (index_select / memcpy release the GIL) so the training thread only
         # ever launches work; depth is bounded by the number of pinned slots
         self.background = bool(background) and self.pin
+        self.workers = max(1, int(workers))
         # set by DevicePrefetcher: event that fires when the async H2D copy out of a pinned slot is done
         self.slot_events: List[Optional["torch.cuda.Event"]] = [None] * num_slots
         self.last_slot = 0
@@ -81,59 +75,85 @@ class BatchLoader:
             self._slots[slot] = cur
         return cur
 
+    def _index_batches(self) -> List[List[int]]:
+        out: List[List[int]] = []
+        cur: List[int] = []
+        for idx in self.sampler:
+            cur.append(idx)
+            if len(cur) == self.batch_size:
+                out.append(cur)
+                cur = []
+        if cur and not self.drop_last:
+            out.append(cur)
+        return out
+
     def __iter__(self) -> Iterator[Tuple[torch.Tensor, ...]]:
+        batches = self._index_batches()
         if not self.background:
-            yield from self._produce()
+            for k, idxs in enumerate(batches):
+                yield self._make(idxs, k % self.num_slots)
             return
-        q: "queue.Queue" = queue.Queue(maxsize=max(1, self.num_slots - 3))
-        stop = threading.Event()
-        END = object()
+        # `workers` helper threads gather whole batches into the rotating pinned slots (index_select / memcpy release
+        # the GIL); batch k always lands in slot k % num_slots and is handed out in order.  A worker may run at most
+        # `window` batches ahead of the consumer, so a slot is never refilled before its previous batch was taken
+        # (and `_make` additionally waits for that batch's H2D copy to finish).
+        n = len(batches)
+        window = max(1, self.num_slots - 3)
+        cv = threading.Condition()
+        state = {"next": 0, "taken": 0, "stop": False, "err": None}
+        ready = {}
 
         def work():
-            try:
-                for item in self._produce():
-                    while not stop.is_set():
-                        try:
-                            q.put(item, timeout=0.1)
-                            break
-                        except queue.Full:
-                            continue
-                    if stop.is_set():
+            while True:
+                with cv:
+                    while not state["stop"] and state["next"] < n and state["next"] >= state["taken"] + window:
+                        cv.wait(0.05)
+                    if state["stop"] or state["next"] >= n:
                         return
-                q.put(END)
-            except BaseException as exc:   # surface loader errors in the consumer
-                q.put(exc)
+                    k = state["next"]
+                    state["next"] += 1
+                try:
+                    item = self._make(batches[k], k % self.num_slots)
+                except BaseException as exc:      # surface loader errors in the consumer
+                    with cv:
+                        state["err"] = exc
+                        cv.notify_all()
+                    return
+                with cv:
+                    ready[k] = item
+                    cv.notify_all()
 
-        t = threading.Thread(target=work, name="b200ddp-batch-loader", daemon=True)
-        t.start()
-        entry = (stop, q, t)
+        threads = [threading.Thread(target=work, name=f"b200ddp-batch-loader-{i}", daemon=True) for i in range(self.workers)]
+        for t in threads:
+            t.start()
+
+        class _Entry:
+            def stop(self_inner):
+                with cv:
+                    state["stop"] = True
+                    cv.notify_all()
+                for t in threads:
+                    t.join(timeout=2.0)
+
+        entry = _Entry()
         with _ACTIVE_LOCK:
             _ACTIVE.append(entry)
         try:
-            while True:
-                item = q.get()
-                if item is END:
-                    break
-                if isinstance(item, BaseException):
-                    raise item
+            for k in range(n):
+                with cv:
+                    while k not in ready and state["err"] is None:
+                        cv.wait(0.05)
+                    if state["err"] is not None:
+                        raise state["err"]
+                    item = ready.pop(k)
+                    state["taken"] = k + 1
+                    cv.notify_all()
                 yield item
         finally:
             with _ACTIVE_LOCK:
                 if entry in _ACTIVE:
                     _ACTIVE.remove(entry)
-            _stop_helper(entry)       # unblock a producer waiting on a full queue, wait for it to leave native code
-
-    def _produce(self) -> Iterator[Tuple[torch.Tensor, ...]]:
-        indices: List[int] = []
-        slot = 0
-        for idx in self.sampler:
-            indices.append(idx)
-            if len(indices) == self.batch_size:
-                yield self._make(indices, slot)
-                slot = (slot + 1) % self.num_slots
-                indices = []
-        if indices and not self.drop_last:
-            yield self._make(indices, slot)
+            entry.stop()
 
     def _tag(self, fields, slot: int):
         b = PinnedBatch(fields)

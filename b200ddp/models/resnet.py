@@ -9,7 +9,7 @@ from typing import List
 import torch
 import torch.nn as nn
 
-from ..ops import FusedBatchNormAct2d, Linear
+from ..ops import FusedBatchNormAct2d, Linear, MaxPool3x3s2
 
 
 class Bottleneck(nn.Module):
@@ -39,7 +39,7 @@ class ResNet(nn.Module):
         self.inplanes = 64
         self.conv1 = nn.Conv2d(3, 64, 7, stride=2, padding=3, bias=False)
         self.bn1 = FusedBatchNormAct2d(64, relu=True)
-        self.maxpool = nn.MaxPool2d(3, stride=2, padding=1)
+        self.maxpool = MaxPool3x3s2()
         self.layer1 = self._make_layer(64, layers[0], 1)
         self.layer2 = self._make_layer(128, layers[1], 2)
         self.layer3 = self._make_layer(256, layers[2], 2)

@@ -76,3 +76,27 @@ class FusedBatchNormAct2d(nn.BatchNorm2d):
 
     def extra_repr(self) -> str:
         return super().extra_repr() + f", relu={self.relu}"
+
+
+class _MaxPool3x3s2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        y, idx = _ext.get().maxpool3x3s2_fwd(x)
+        ctx.save_for_backward(idx)
+        ctx.hw = (x.shape[2], x.shape[3])
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (idx,) = ctx.saved_tensors
+        return _ext.get().maxpool3x3s2_bwd(dy, idx, ctx.hw[0], ctx.hw[1])
+
+
+class MaxPool3x3s2(nn.Module):
+    """``nn.MaxPool2d(3, stride=2, padding=1)`` (the ResNet stem pool) with native channels_last kernels on CUDA."""
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if (x.is_cuda and x.dim() == 4 and x.shape[1] % 8 == 0 and x.dtype in (torch.bfloat16, torch.float32)
+                and x.is_contiguous(memory_format=torch.channels_last)):
+            return _MaxPool3x3s2.apply(x)
+        return F.max_pool2d(x, 3, stride=2, padding=1)

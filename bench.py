@@ -305,8 +305,11 @@ def run_ours(args):
         e0.record()
         h2d_bytes = 0
         d2h_bytes = 0
+        wait_s = 0.0
         for i in range(args.steps):
+            t_w = time.perf_counter()
             (x, y), feed = next(stream)
+            wait_s += time.perf_counter() - t_w
             h2d_bytes += x.numel() * x.element_size() + y.numel() * y.element_size()
             loss = step(x, y)
             sched.step()
@@ -317,7 +320,8 @@ def run_ours(args):
         sync_all()
         ms_e2e = e0.elapsed_time(e1)
         last_loss = float(loss_ring[(args.steps - 1) % len(loss_ring)])
-        e2e = {"ms": ms_e2e, "h2d": h2d_bytes / args.steps, "d2h": d2h_bytes / args.steps, "last_loss": last_loss}
+        e2e = {"ms": ms_e2e, "h2d": h2d_bytes / args.steps, "d2h": d2h_bytes / args.steps, "last_loss": last_loss,
+               "loader_wait_ms": wait_s * 1e3 / args.steps}
 
     # ---- reduce over ranks (max time) ---------------------------------------------------------------
     def max_over_ranks(v):
@@ -350,7 +354,8 @@ def run_ours(args):
         if e2e:
             out["e2e"] = {"value": global_batch * args.steps / (e2e["ms"] / 1e3), "unit": "samples/s",
                           "ms_per_step": e2e["ms"] / args.steps, "h2d_bytes_per_step": e2e["h2d"],
-                          "d2h_bytes_per_step": e2e["d2h"], "last_loss": e2e["last_loss"]}
+                          "d2h_bytes_per_step": e2e["d2h"], "last_loss": e2e["last_loss"],
+                          "host_wait_for_batch_ms_per_step": e2e["loader_wait_ms"]}
         emit(out)
     stream.close()                      # stops the loader's helper thread before interpreter shutdown
     if world > 1:

@@ -88,3 +88,19 @@ def test_resnet50_fused_matches_stock_modules():
         assert rel < 3e-2, (n, rel)
     for (n, p), q in zip(ours.named_buffers(), stock.buffers()):
         assert torch.allclose(p.float(), q.float(), atol=1e-3, rtol=1e-3), n
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(32, 64, 112, 112), (2, 8, 7, 9), (3, 16, 6, 6), (1, 8, 1, 1)])
+def test_maxpool3x3s2_matches_torch(dtype, shape):
+    from b200ddp.ops import MaxPool3x3s2
+    torch.manual_seed(0)
+    x = torch.randn(*shape, device="cuda").to(dtype).contiguous(memory_format=torch.channels_last).requires_grad_()
+    y = MaxPool3x3s2()(x)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    xr = x.detach().clone().requires_grad_()
+    yr = F.max_pool2d(xr, 3, stride=2, padding=1)
+    yr.backward(dy)
+    assert torch.equal(y, yr)
+    assert torch.allclose(x.grad.float(), xr.grad.float(), atol=1e-2 if dtype == torch.bfloat16 else 1e-6)
