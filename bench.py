@@ -442,7 +442,8 @@ def run_reference(args):
         def __init__(self, samples):   # the reference calls FooDataset(100000)
             super().__init__(samples=args.samples, size=args.image_size, image_dtype=torch.float32, dense_target=True)
 
-    ref.FooDataset = RefDataset        # dataset.py is the template's customisation point; no source edit
+    if args.model != "foo":
+        ref.FooDataset = RefDataset    # dataset.py is the template's customisation point; no source edit
 
     ns = argparse.Namespace(**{"global_step": 0, "no_cuda": False, "output_dir": "/tmp/ref_outputs", "seed": 42,
                                "gradient_accumulation_steps": 1, "per_gpu_train_batch_size": args.per_gpu_batch,
@@ -455,7 +456,11 @@ def run_reference(args):
     os.chdir("/tmp/ref_run")           # SummaryWriter() writes ./runs
     with contextlib.redirect_stdout(sys.stderr):
         ref.setup(ns)
-        model = RefWorkload()
+        if args.model == "foo":
+            import model as ref_model_mod          # the reference's own model.py (FooModel) and dataset.py, untouched
+            model = ref_model_mod.FooModel()
+        else:
+            model = RefWorkload()
         model.register_forward_pre_hook(pre_hook)
         ref.train(ns, model)
     os.chdir(cwd)
@@ -468,10 +473,10 @@ def run_reference(args):
         ref.cleanup(ns)
     global_batch = args.per_gpu_batch * world
     value = global_batch * K / (ms / 1e3)
-    target_bytes = args.per_gpu_batch * 1000 * 4
+    target_bytes = args.per_gpu_batch * (5 if args.model == "foo" else 1000) * 4
     if rank == 0:
         emit({"metric": "samples/sec (whole box, device-timed, max over ranks) for ResNet-50 DDP at 1/2/4/8 B200",
-              "impl": "reference", "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
+              "impl": "reference", "model": args.model, "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
               "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
               "data": "synthetic (random-init weights, random ImageNet-shaped batches via the reference DataLoader, pin_memory)",
               "config": config_dict(args, world, {"transport": "nccl (stock torch DDP)" if world > 1 else "single",
