@@ -18,6 +18,8 @@
 // channel tile finishes the reduction in a fixed order (no float atomics -> bitwise reproducible).
 #include "ops.h"
 
+#include <cstdlib>
+
 namespace b200 {
 namespace {
 
@@ -69,15 +71,46 @@ __device__ __forceinline__ void reduce_rows(float (*acc)[kVec], float* smem, int
 
 // ------------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const T* __restrict__ x, int R, int C, int cvb, int ty,
+__device__ __forceinline__ void bn_apply_rows(const T* __restrict__ x, const T* __restrict__ residual, T* __restrict__ y,
+                                              unsigned char* __restrict__ mask, const float* __restrict__ scale,
+                                              const float* __restrict__ shift, int C, int cv, int r0, int r1, int tyi, int ty, int relu);
+
+// release/acquire on the per-tile generation word used by the fused (single-launch) variants
+__device__ __forceinline__ void bn_st_release(unsigned int* p, unsigned int v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned int bn_ld_acquire(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// bounded spin (2 s): a scheduling surprise must degrade into a wrong number, never into a hung GPU
+__device__ __forceinline__ void bn_wait_generation(const unsigned int* p, unsigned int gen0) {
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  while (bn_ld_acquire(p) == gen0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (t - t0 > 2000000000ull) break;
+  }
+}
+
+// FUSED = true: statistics AND normalisation in ONE launch.  All blocks of a channel tile rendezvous on a
+// generation word after the tile's last block has finished the statistics (the grid is sized to be co-resident:
+// <= 2 blocks per SM), then every block normalises exactly the rows it has just read (L2-hot).
+template <typename T, bool FUSED>
+__global__ void __launch_bounds__(kBnThreads, 2) bn_stats_kernel(const T* __restrict__ x, int R, int C, int cvb, int ty,
                                                              float* __restrict__ partial /*[2][S][C]*/, unsigned int* __restrict__ counters,
                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
                                                              float* __restrict__ running_mean, float* __restrict__ running_var,
                                                              long long* __restrict__ num_batches, float* __restrict__ save_mean,
                                                              float* __restrict__ save_rstd, float* __restrict__ scale, float* __restrict__ shift,
-                                                             float eps, float momentum) {
+                                                             float eps, float momentum, const T* __restrict__ residual, T* __restrict__ y,
+                                                             unsigned char* __restrict__ mask, int relu) {
   extern __shared__ float smem[];
   __shared__ bool is_last;
+  unsigned int* gen = counters + gridDim.x;             // [grid_x] generation words behind the [grid_x] ticket counters
+  unsigned int gen0 = 0;
+  if (FUSED && threadIdx.x == 0) gen0 = *reinterpret_cast<volatile unsigned int*>(&gen[blockIdx.x]);   // read BEFORE taking a ticket
   const int tx = threadIdx.x % cvb, tyi = threadIdx.x / cvb;
   const int cv = blockIdx.x * cvb + tx;                 // channel-vector index
   const int S = gridDim.y;
@@ -121,58 +154,61 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const T* __restric
     is_last = (ticket == (unsigned int)S - 1);
   }
   __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  const float inv_r = 1.f / (float)R;
-  // finish: `lanes` threads per channel each sum a strided subset of the S partials (independent loads in flight),
-  // then a fixed-order combine through shared memory
-  const int lanes = max(1, (int)blockDim.x / width);
-  {
-    const int c = threadIdx.x % width, l = threadIdx.x / width;
-    float ps = 0.f, pq = 0.f;
-    if (l < lanes && c0 + c < C) {
-#pragma unroll 4
-      for (int k = l; k < S; k += lanes) { ps += __ldcg(&partial[(size_t)(0 * S + k) * C + c0 + c]); pq += __ldcg(&partial[(size_t)(1 * S + k) * C + c0 + c]); }
+  if (!FUSED && !is_last) return;
+  if (is_last) {
+    __threadfence();
+    const float inv_r = 1.f / (float)R;
+    // finish: `lanes` threads per channel each sum a strided subset of the S partials (independent loads in flight),
+    // then a fixed-order combine through shared memory
+    const int lanes = max(1, (int)blockDim.x / width);
+    {
+      const int c = threadIdx.x % width, l = threadIdx.x / width;
+      float ps = 0.f, pq = 0.f;
+      if (l < lanes && c0 + c < C) {
+  #pragma unroll 4
+        for (int k = l; k < S; k += lanes) { ps += __ldcg(&partial[(size_t)(0 * S + k) * C + c0 + c]); pq += __ldcg(&partial[(size_t)(1 * S + k) * C + c0 + c]); }
+      }
+      __syncthreads();
+      if (l < lanes) { smem[l * width + c] = ps; smem[(lanes + l) * width + c] = pq; }
+      __syncthreads();
     }
+    for (int c = threadIdx.x; c < width; c += blockDim.x) {
+      const int ch = c0 + c;
+      if (ch >= C) continue;
+      float s = 0.f, q = 0.f;
+      for (int l = 0; l < lanes; ++l) { s += smem[l * width + c]; q += smem[(lanes + l) * width + c]; }
+      const float mean = s * inv_r;
+      const float var = fmaxf(q * inv_r - mean * mean, 0.f);     // biased variance (normalisation)
+      const float rstd = rsqrtf(var + eps);
+      const float sc = gamma[ch] * rstd;
+      save_mean[ch] = mean;
+      save_rstd[ch] = rstd;
+      scale[ch] = sc;
+      shift[ch] = beta[ch] - mean * sc;
+      if (running_mean != nullptr) {
+        const float unbiased = R > 1 ? var * ((float)R / (float)(R - 1)) : var;
+        running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * mean;
+        running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * unbiased;
+      }
+    }
+
     __syncthreads();
-    if (l < lanes) { smem[l * width + c] = ps; smem[(lanes + l) * width + c] = pq; }
-    __syncthreads();
-  }
-  for (int c = threadIdx.x; c < width; c += blockDim.x) {
-    const int ch = c0 + c;
-    if (ch >= C) continue;
-    float s = 0.f, q = 0.f;
-    for (int l = 0; l < lanes; ++l) { s += smem[l * width + c]; q += smem[(lanes + l) * width + c]; }
-    const float mean = s * inv_r;
-    const float var = fmaxf(q * inv_r - mean * mean, 0.f);     // biased variance (normalisation)
-    const float rstd = rsqrtf(var + eps);
-    const float sc = gamma[ch] * rstd;
-    save_mean[ch] = mean;
-    save_rstd[ch] = rstd;
-    scale[ch] = sc;
-    shift[ch] = beta[ch] - mean * sc;
-    if (running_mean != nullptr) {
-      const float unbiased = R > 1 ? var * ((float)R / (float)(R - 1)) : var;
-      running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * mean;
-      running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * unbiased;
+    if (threadIdx.x == 0) {
+      counters[blockIdx.x] = 0u;                                 // ready for the next launch (graph replay safe)
+      if (blockIdx.x == 0 && num_batches != nullptr) *num_batches += 1;
+      if (FUSED) { __threadfence(); bn_st_release(&gen[blockIdx.x], gen0 + 1u); }
     }
   }
-  if (threadIdx.x == 0) {
-    counters[blockIdx.x] = 0u;                                   // ready for the next launch (graph replay safe)
-    if (blockIdx.x == 0 && num_batches != nullptr) *num_batches += 1;
-  }
+  if (!FUSED) return;
+  if (!is_last && threadIdx.x == 0) bn_wait_generation(&gen[blockIdx.x], gen0);      // the tile's statistics are final
+  __syncthreads();
+  if (cv * kVec < C) bn_apply_rows<T>(x, residual, y, mask, scale, shift, C, cv, r0, r1, tyi, ty, relu);
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ residual, T* __restrict__ y,
-                                                             unsigned char* __restrict__ mask, const float* __restrict__ scale,
-                                                             const float* __restrict__ shift, int R, int C, int cvb, int ty, int relu) {
-  const int tx = threadIdx.x % cvb, tyi = threadIdx.x / cvb;
-  const int cv = blockIdx.x * cvb + tx;
-  if (cv * kVec >= C) return;
-  const int S = gridDim.y;
-  const int rows_per = (R + S - 1) / S;
-  const int r0 = blockIdx.y * rows_per, r1 = min(R, r0 + rows_per);
+__device__ __forceinline__ void bn_apply_rows(const T* __restrict__ x, const T* __restrict__ residual, T* __restrict__ y,
+                                              unsigned char* __restrict__ mask, const float* __restrict__ scale,
+                                              const float* __restrict__ shift, int C, int cv, int r0, int r1, int tyi, int ty, int relu) {
   float sc[kVec], sh[kVec];                       // per-channel constants stay in registers for the whole row loop
   bn_load8<float>(scale + cv * kVec, sc);
   bn_load8<float>(shift + cv * kVec, sh);
@@ -187,7 +223,6 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const T* __restric
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-#pragma unroll
       unsigned int bits = 0;
 #pragma unroll
       for (int i = 0; i < kVec; ++i) {
@@ -204,7 +239,6 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const T* __restric
     float f[kVec], rs[kVec];
     bn_load8<T>(x + (size_t)r * C + col, f);
     if (residual != nullptr) bn_load8<T>(residual + (size_t)r * C + col, rs);
-#pragma unroll
     unsigned int bits = 0;
 #pragma unroll
     for (int i = 0; i < kVec; ++i) {
@@ -218,15 +252,38 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const T* __restric
   }
 }
 
-// ------------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const unsigned char* __restrict__ y,
-                                                                  int R, int C, int cvb, int ty, int relu, const float* __restrict__ save_mean,
-                                                                  const float* __restrict__ save_rstd, float* __restrict__ partial,
-                                                                  unsigned int* __restrict__ counters, float* __restrict__ dgamma,
-                                                                  float* __restrict__ dbeta, float* __restrict__ coef /*[2][C]*/) {
+__global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ residual, T* __restrict__ y,
+                                                             unsigned char* __restrict__ mask, const float* __restrict__ scale,
+                                                             const float* __restrict__ shift, int R, int C, int cvb, int ty, int relu) {
+  const int tx = threadIdx.x % cvb, tyi = threadIdx.x / cvb;
+  const int cv = blockIdx.x * cvb + tx;
+  if (cv * kVec >= C) return;
+  const int S = gridDim.y;
+  const int rows_per = (R + S - 1) / S;
+  const int r0 = blockIdx.y * rows_per, r1 = min(R, r0 + rows_per);
+  bn_apply_rows<T>(x, residual, y, mask, scale, shift, C, cv, r0, r1, tyi, ty, relu);
+}
+
+template <typename T>
+__device__ __forceinline__ void bn_bwd_apply_rows(const T* __restrict__ dy, const T* __restrict__ x, const unsigned char* __restrict__ y,
+                                                  T* __restrict__ dx, T* __restrict__ dres, const float* __restrict__ save_mean,
+                                                  const float* __restrict__ save_rstd, const float* __restrict__ gamma,
+                                                  const float* __restrict__ coef, int C, int cv, int r0, int r1, int tyi, int ty, int relu);
+
+// ------------------------------------------------------------------------------------------------------
+template <typename T, bool FUSED>
+__global__ void __launch_bounds__(kBnThreads, 2) bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const unsigned char* __restrict__ y,
+                                                                     int R, int C, int cvb, int ty, int relu, const float* __restrict__ save_mean,
+                                                                     const float* __restrict__ save_rstd, float* __restrict__ partial,
+                                                                     unsigned int* __restrict__ counters, float* __restrict__ dgamma,
+                                                                     float* __restrict__ dbeta, float* __restrict__ coef /*[2][C]*/,
+                                                                     const float* __restrict__ gamma, T* __restrict__ dx, T* __restrict__ dres) {
   extern __shared__ float smem[];
   __shared__ bool is_last;
+  unsigned int* gen = counters + gridDim.x;
+  unsigned int gen0 = 0;
+  if (FUSED && threadIdx.x == 0) gen0 = *reinterpret_cast<volatile unsigned int*>(&gen[blockIdx.x]);
   const int tx = threadIdx.x % cvb, tyi = threadIdx.x / cvb;
   const int cv = blockIdx.x * cvb + tx;
   const int S = gridDim.y;
@@ -290,47 +347,52 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(const T* __re
     is_last = (ticket == (unsigned int)S - 1);
   }
   __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  const float inv_r = 1.f / (float)R;
-  // finish: `lanes` threads per channel each sum a strided subset of the S partials (independent loads in flight),
-  // then a fixed-order combine through shared memory
-  const int lanes = max(1, (int)blockDim.x / width);
-  {
-    const int c = threadIdx.x % width, l = threadIdx.x / width;
-    float ps = 0.f, pq = 0.f;
-    if (l < lanes && c0 + c < C) {
-#pragma unroll 4
-      for (int k = l; k < S; k += lanes) { ps += __ldcg(&partial[(size_t)(0 * S + k) * C + c0 + c]); pq += __ldcg(&partial[(size_t)(1 * S + k) * C + c0 + c]); }
+  if (!FUSED && !is_last) return;
+  if (is_last) {
+    __threadfence();
+    const float inv_r = 1.f / (float)R;
+    // finish: `lanes` threads per channel each sum a strided subset of the S partials (independent loads in flight),
+    // then a fixed-order combine through shared memory
+    const int lanes = max(1, (int)blockDim.x / width);
+    {
+      const int c = threadIdx.x % width, l = threadIdx.x / width;
+      float ps = 0.f, pq = 0.f;
+      if (l < lanes && c0 + c < C) {
+  #pragma unroll 4
+        for (int k = l; k < S; k += lanes) { ps += __ldcg(&partial[(size_t)(0 * S + k) * C + c0 + c]); pq += __ldcg(&partial[(size_t)(1 * S + k) * C + c0 + c]); }
+      }
+      __syncthreads();
+      if (l < lanes) { smem[l * width + c] = ps; smem[(lanes + l) * width + c] = pq; }
+      __syncthreads();
     }
+    for (int c = threadIdx.x; c < width; c += blockDim.x) {
+      const int ch = c0 + c;
+      if (ch >= C) continue;
+      float s = 0.f, q = 0.f;
+      for (int l = 0; l < lanes; ++l) { s += smem[l * width + c]; q += smem[(lanes + l) * width + c]; }
+      dbeta[ch] = s;
+      dgamma[ch] = q;
+      coef[ch] = s * inv_r;            // mean(dy*)
+      coef[C + ch] = q * inv_r;        // mean(dy* xhat)
+    }
+
     __syncthreads();
-    if (l < lanes) { smem[l * width + c] = ps; smem[(lanes + l) * width + c] = pq; }
-    __syncthreads();
+    if (threadIdx.x == 0) {
+      counters[blockIdx.x] = 0u;
+      if (FUSED) { __threadfence(); bn_st_release(&gen[blockIdx.x], gen0 + 1u); }
+    }
   }
-  for (int c = threadIdx.x; c < width; c += blockDim.x) {
-    const int ch = c0 + c;
-    if (ch >= C) continue;
-    float s = 0.f, q = 0.f;
-    for (int l = 0; l < lanes; ++l) { s += smem[l * width + c]; q += smem[(lanes + l) * width + c]; }
-    dbeta[ch] = s;
-    dgamma[ch] = q;
-    coef[ch] = s * inv_r;            // mean(dy*)
-    coef[C + ch] = q * inv_r;        // mean(dy* xhat)
-  }
-  if (threadIdx.x == 0) counters[blockIdx.x] = 0u;
+  if (!FUSED) return;
+  if (!is_last && threadIdx.x == 0) bn_wait_generation(&gen[blockIdx.x], gen0);
+  __syncthreads();
+  if (cv * kVec < C) bn_bwd_apply_rows<T>(dy, x, y, dx, dres, save_mean, save_rstd, gamma, coef, C, cv, r0, r1, tyi, ty, relu);
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const unsigned char* __restrict__ y,
-                                                                 T* __restrict__ dx, T* __restrict__ dres, const float* __restrict__ save_mean,
-                                                                 const float* __restrict__ save_rstd, const float* __restrict__ gamma,
-                                                                 const float* __restrict__ coef, int R, int C, int cvb, int ty, int relu) {
-  const int tx = threadIdx.x % cvb, tyi = threadIdx.x / cvb;
-  const int cv = blockIdx.x * cvb + tx;
-  if (cv * kVec >= C) return;
-  const int S = gridDim.y;
-  const int rows_per = (R + S - 1) / S;
-  const int r0 = blockIdx.y * rows_per, r1 = min(R, r0 + rows_per);
+__device__ __forceinline__ void bn_bwd_apply_rows(const T* __restrict__ dy, const T* __restrict__ x, const unsigned char* __restrict__ y,
+                                                  T* __restrict__ dx, T* __restrict__ dres, const float* __restrict__ save_mean,
+                                                  const float* __restrict__ save_rstd, const float* __restrict__ gamma,
+                                                  const float* __restrict__ coef, int C, int cv, int r0, int r1, int tyi, int ty, int relu) {
   // dx = a*dy* + b*x + c  with per-channel a = gamma*rstd, b = -a*rstd*c2, c = -a*(c1 - mean*rstd*c2)
   float ka[kVec], kb[kVec], kc[kVec];
   {
@@ -388,6 +450,20 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const T* __res
   }
 }
 
+template <typename T>
+__global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const unsigned char* __restrict__ y,
+                                                                 T* __restrict__ dx, T* __restrict__ dres, const float* __restrict__ save_mean,
+                                                                 const float* __restrict__ save_rstd, const float* __restrict__ gamma,
+                                                                 const float* __restrict__ coef, int R, int C, int cvb, int ty, int relu) {
+  const int tx = threadIdx.x % cvb, tyi = threadIdx.x / cvb;
+  const int cv = blockIdx.x * cvb + tx;
+  if (cv * kVec >= C) return;
+  const int S = gridDim.y;
+  const int rows_per = (R + S - 1) / S;
+  const int r0 = blockIdx.y * rows_per, r1 = min(R, r0 + rows_per);
+  bn_bwd_apply_rows<T>(dy, x, y, dx, dres, save_mean, save_rstd, gamma, coef, C, cv, r0, r1, tyi, ty, relu);
+}
+
 Tile pick_tile(int R, int C) {
   Tile t;
   const int cv = C / kVec;
@@ -413,12 +489,24 @@ dim3 apply_grid(const Tile& t, int R) {
   return dim3(t.grid_x, gy);
 }
 
+// Fused (single-launch) variants need every block of a channel tile resident at once: cap the grid at 2 blocks per SM.
+bool fused_tile(int R, int C, Tile* t) {
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("B200DDP_BN_FUSED"); enabled = (e && atoi(e) == 0) ? 0 : 1; }
+  *t = pick_tile(R, C);
+  if (!enabled || t->grid_x > 2 * kNumSMs) return false;
+  int cap = (2 * kNumSMs) / t->grid_x;
+  if (cap < 1) cap = 1;
+  if (t->grid_y > cap) t->grid_y = cap;
+  return true;
+}
+
 }  // namespace
 
 void bn_workspace_sizes(int R, int C, size_t* partial_floats, size_t* counters) {
   const Tile t = pick_tile(R, C);
   *partial_floats = (size_t)2 * t.grid_y * C;
-  *counters = (size_t)t.grid_x;
+  *counters = (size_t)2 * t.grid_x;          // tickets + generation words
 }
 
 void launch_bn_forward(const void* x, const void* residual, void* y, unsigned char* mask, DType dt, int R, int C, const float* gamma, const float* beta,
@@ -426,22 +514,26 @@ void launch_bn_forward(const void* x, const void* residual, void* y, unsigned ch
                        float* scale, float* shift, float* partial, unsigned int* counters, float eps, float momentum, bool relu,
                        cudaStream_t s) {
   if (C % kVec != 0) throw std::runtime_error("fused batch norm: channel count must be a multiple of 8");
-  const Tile t = pick_tile(R, C);
+  Tile t;
+  const bool fused = fused_tile(R, C, &t);
   const size_t smem = (size_t)2 * t.ty * t.cvb * kVec * sizeof(float);
   const dim3 grid(t.grid_x, t.grid_y);
-  if (dt == DType::BF16) {
-    bn_stats_kernel<__nv_bfloat16><<<grid, kBnThreads, smem, s>>>((const __nv_bfloat16*)x, R, C, t.cvb, t.ty, partial, counters, gamma, beta,
-                                                                  running_mean, running_var, num_batches, save_mean, save_rstd, scale, shift, eps, momentum);
-    B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
+  const int r = relu ? 1 : 0;
+#define B200_BN_FWD(T, F)                                                                                                            \
+  bn_stats_kernel<T, F><<<grid, kBnThreads, smem, s>>>((const T*)x, R, C, t.cvb, t.ty, partial, counters, gamma, beta, running_mean, \
+                                                       running_var, num_batches, save_mean, save_rstd, scale, shift, eps, momentum, \
+                                                       (const T*)residual, (T*)y, mask, r)
+  if (dt == DType::BF16) { if (fused) B200_BN_FWD(__nv_bfloat16, true); else B200_BN_FWD(__nv_bfloat16, false); }
+  else { if (fused) B200_BN_FWD(float, true); else B200_BN_FWD(float, false); }
+#undef B200_BN_FWD
+  B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
+  if (fused) return;
+  if (dt == DType::BF16)
     bn_apply_kernel<__nv_bfloat16><<<apply_grid(t, R), kBnThreads, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)residual,
-                                                                           (__nv_bfloat16*)y, mask, scale, shift, R, C, t.cvb, t.ty, relu ? 1 : 0);
-  } else {
-    bn_stats_kernel<float><<<grid, kBnThreads, smem, s>>>((const float*)x, R, C, t.cvb, t.ty, partial, counters, gamma, beta, running_mean,
-                                                          running_var, num_batches, save_mean, save_rstd, scale, shift, eps, momentum);
-    B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
+                                                                           (__nv_bfloat16*)y, mask, scale, shift, R, C, t.cvb, t.ty, r);
+  else
     bn_apply_kernel<float><<<apply_grid(t, R), kBnThreads, 0, s>>>((const float*)x, (const float*)residual, (float*)y, mask, scale, shift, R, C,
-                                                                   t.cvb, t.ty, relu ? 1 : 0);
-  }
+                                                                   t.cvb, t.ty, r);
   B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
 }
 
@@ -449,23 +541,27 @@ void launch_bn_backward(const void* dy, const void* x, const void* y, void* dx, 
                         const float* save_mean, const float* save_rstd, float* dgamma, float* dbeta, float* coef, float* partial,
                         unsigned int* counters, bool relu, cudaStream_t s) {
   if (C % kVec != 0) throw std::runtime_error("fused batch norm: channel count must be a multiple of 8");
-  const Tile t = pick_tile(R, C);
+  Tile t;
+  const bool fused = fused_tile(R, C, &t);
   const size_t smem = (size_t)2 * t.ty * t.cvb * kVec * sizeof(float);
   const dim3 grid(t.grid_x, t.grid_y);
-  if (dt == DType::BF16) {
-    bn_bwd_reduce_kernel<__nv_bfloat16><<<grid, kBnThreads, smem, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const unsigned char*)y, R, C,
-                                                                       t.cvb, t.ty, relu ? 1 : 0, save_mean, save_rstd, partial, counters, dgamma, dbeta, coef);
-    B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
-    bn_bwd_apply_kernel<__nv_bfloat16><<<apply_grid(t, R), kBnThreads, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,
-                                                                               (const unsigned char*)y, (__nv_bfloat16*)dx, (__nv_bfloat16*)dres,
-                                                                               save_mean, save_rstd, gamma, coef, R, C, t.cvb, t.ty, relu ? 1 : 0);
-  } else {
-    bn_bwd_reduce_kernel<float><<<grid, kBnThreads, smem, s>>>((const float*)dy, (const float*)x, (const unsigned char*)y, R, C, t.cvb, t.ty, relu ? 1 : 0,
-                                                               save_mean, save_rstd, partial, counters, dgamma, dbeta, coef);
-    B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
+  const int r = relu ? 1 : 0;
+#define B200_BN_BWD(T, F)                                                                                                              \
+  bn_bwd_reduce_kernel<T, F><<<grid, kBnThreads, smem, s>>>((const T*)dy, (const T*)x, (const unsigned char*)y, R, C, t.cvb, t.ty, r,  \
+                                                            save_mean, save_rstd, partial, counters, dgamma, dbeta, coef, gamma,      \
+                                                            (T*)dx, (T*)dres)
+  if (dt == DType::BF16) { if (fused) B200_BN_BWD(__nv_bfloat16, true); else B200_BN_BWD(__nv_bfloat16, false); }
+  else { if (fused) B200_BN_BWD(float, true); else B200_BN_BWD(float, false); }
+#undef B200_BN_BWD
+  B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
+  if (fused) return;
+  if (dt == DType::BF16)
+    bn_bwd_apply_kernel<__nv_bfloat16><<<apply_grid(t, R), kBnThreads, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const unsigned char*)y,
+                                                                               (__nv_bfloat16*)dx, (__nv_bfloat16*)dres, save_mean, save_rstd, gamma, coef,
+                                                                               R, C, t.cvb, t.ty, r);
+  else
     bn_bwd_apply_kernel<float><<<apply_grid(t, R), kBnThreads, 0, s>>>((const float*)dy, (const float*)x, (const unsigned char*)y, (float*)dx,
-                                                                       (float*)dres, save_mean, save_rstd, gamma, coef, R, C, t.cvb, t.ty, relu ? 1 : 0);
-  }
+                                                                       (float*)dres, save_mean, save_rstd, gamma, coef, R, C, t.cvb, t.ty, r);
   B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
 }
 

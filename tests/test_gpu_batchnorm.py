@@ -36,11 +36,11 @@ def test_fused_batchnorm_fwd_bwd(dtype, shape, relu, residual):
         bn.bias.uniform_(-0.5, 0.5)
     before = C.launch_count()
     y = bn(x, residual=res) if residual else bn(x)
-    assert C.launch_count() - before == 2, "forward must be exactly two native launches"
+    assert C.launch_count() - before in (1, 2), "forward = one fused launch (or stats + apply)"
     assert y.dtype == dtype and y.is_contiguous(memory_format=torch.channels_last)
     dy = torch.randn_like(y)
     y.backward(dy)
-    assert C.launch_count() - before == 4
+    assert C.launch_count() - before in (2, 4)
     xr, rr, wr, br, rm, rv, yr = _reference(x, res, bn.weight, bn.bias, relu)
     yr.backward(dy.float())
     tol = 2e-4 if dtype == torch.float32 else 4e-2
