@@ -492,7 +492,9 @@ dim3 apply_grid(const Tile& t, int R) {
 // Fused (single-launch) variants need every block of a channel tile resident at once: cap the grid at 2 blocks per SM.
 bool fused_tile(int R, int C, Tile* t) {
   static int enabled = -1;
-  if (enabled < 0) { const char* e = getenv("B200DDP_BN_FUSED"); enabled = (e && atoi(e) == 0) ? 0 : 1; }
+  // measured (profiles/README.md): one launch per direction is NOT faster than two at batch 32 (the co-residency cap
+  // on the grid costs what the saved launch gains), so the two-launch form stays the default; opt in with =1
+  if (enabled < 0) { const char* e = getenv("B200DDP_BN_FUSED"); enabled = (e && atoi(e) == 1) ? 1 : 0; }
   *t = pick_tile(R, C);
   if (!enabled || t->grid_x > 2 * kNumSMs) return false;
   int cap = (2 * kNumSMs) / t->grid_x;

@@ -11,6 +11,12 @@ for tool in memcheck racecheck synccheck; do
   timeout 1200 $SAN --tool $tool --error-exitcode 9 python -m pytest tests/test_gpu_kernels.py -m gpu -q -k "$SEL" > $O/sanitize_${tool}.log 2>&1
   echo "$tool kernels rc=$?" | tee -a $O/sanitize_summary.txt
 done
+echo "== memcheck + racecheck (BatchNorm / pooling kernels)"
+for tool in memcheck racecheck; do
+  timeout 1200 $SAN --tool $tool --error-exitcode 9 python -m pytest tests/test_gpu_batchnorm.py -m gpu -q \
+      -k "shape2 or shape4 or maxpool" > $O/sanitize_bn_${tool}.log 2>&1
+  echo "$tool bn rc=$?" | tee -a $O/sanitize_summary.txt
+done
 echo "== memcheck (tcgen05 GEMM, small shapes)"
 timeout 1200 $SAN --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_gemm.py -m gpu -q -k "test_gemm_operand_layouts or test_gemm_epilogues" > $O/sanitize_gemm_memcheck.log 2>&1
 echo "memcheck gemm rc=$?" | tee -a $O/sanitize_summary.txt
