@@ -325,6 +325,23 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     return std::make_tuple(loss, dlogits);
   });
 
+  m.def("gelu_fwd", [](at::Tensor pre) {
+    check_cuda(pre, "pre");
+    TORCH_CHECK(pre.is_contiguous(), "gelu_fwd: contiguous input");
+    c10::cuda::CUDAGuard guard(pre.device());
+    at::Tensor out = at::empty_like(pre);
+    launch_gelu(pre.data_ptr(), nullptr, out.data_ptr(), dtype_of(pre), (size_t)pre.numel(), false, cur_stream());
+    return out;
+  });
+  m.def("gelu_bwd", [](at::Tensor dy, at::Tensor pre) {
+    check_cuda(pre, "pre");
+    TORCH_CHECK(pre.is_contiguous() && dy.is_contiguous() && dy.dtype() == pre.dtype() && dy.numel() == pre.numel(), "gelu_bwd: matching contiguous tensors");
+    c10::cuda::CUDAGuard guard(pre.device());
+    at::Tensor out = at::empty_like(pre);
+    launch_gelu(pre.data_ptr(), dy.data_ptr(), out.data_ptr(), dtype_of(pre), (size_t)pre.numel(), true, cur_stream());
+    return out;
+  });
+
   // ---- layer norm -------------------------------------------------------------------------------
   m.def("layernorm_fwd", [](at::Tensor x, at::Tensor gamma, at::Tensor beta, double eps) {
     check_cuda(x, "x");

@@ -257,3 +257,59 @@ void launch_xent_fwd_bwd(const void* logits, const long long* targets, DType dt,
 }
 
 }  // namespace b200
+
+// ---------------------------------------------------------------------------------------------------------
+// GELU (erf form) forward and backward as single vectorised passes.  The stock autograd formula for the backward
+// (cast to fp32, erf, exp, three multiplies, cast back) is ~8 launches over a [tokens, 3072] tensor per BERT layer.
+namespace b200 {
+namespace {
+
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
+  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+template <typename T, bool BWD>
+__global__ void __launch_bounds__(kLossThreads) gelu_kernel(const T* __restrict__ pre, const T* __restrict__ dy, T* __restrict__ out, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(pre) | reinterpret_cast<uintptr_t>(out) | (BWD ? reinterpret_cast<uintptr_t>(dy) : 0)) & 31u) == 0;
+  size_t done = 0;
+  if (aligned) {
+    const size_t nvec = n / 8;
+    for (size_t v = tid; v < nvec; v += stride) {
+      float a[8], g[8];
+      loss_load8<T>(pre + v * 8, a);
+      if (BWD) loss_load8<T>(dy + v * 8, g);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = BWD ? g[i] * gelu_grad_f(a[i]) : gelu_f(a[i]);
+      loss_store8<T>(out + v * 8, a);
+    }
+    done = nvec * 8;
+  }
+  for (size_t i = done + tid; i < n; i += stride) {
+    const float x = to_f32<T>(pre[i]);
+    out[i] = from_f32<T>(BWD ? to_f32<T>(dy[i]) * gelu_grad_f(x) : gelu_f(x));
+  }
+}
+
+}  // namespace
+
+void launch_gelu(const void* pre, const void* dy, void* out, DType dt, size_t n, bool backward, cudaStream_t s) {
+  size_t b = (n / 8 + kLossThreads - 1) / kLossThreads;
+  if (b < 1) b = 1;
+  if (b > (size_t)16 * kNumSMs) b = (size_t)16 * kNumSMs;
+  const int blocks = (int)b;
+  if (dt == DType::BF16) {
+    if (backward) gelu_kernel<__nv_bfloat16, true><<<blocks, kLossThreads, 0, s>>>((const __nv_bfloat16*)pre, (const __nv_bfloat16*)dy, (__nv_bfloat16*)out, n);
+    else gelu_kernel<__nv_bfloat16, false><<<blocks, kLossThreads, 0, s>>>((const __nv_bfloat16*)pre, nullptr, (__nv_bfloat16*)out, n);
+  } else {
+    if (backward) gelu_kernel<float, true><<<blocks, kLossThreads, 0, s>>>((const float*)pre, (const float*)dy, (float*)out, n);
+    else gelu_kernel<float, false><<<blocks, kLossThreads, 0, s>>>((const float*)pre, nullptr, (float*)out, n);
+  }
+  B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
+}
+
+}  // namespace b200

@@ -49,6 +49,9 @@ void launch_xent_fwd_bwd(const void* logits, const long long* targets, DType dt,
                          long long ignore_index, float gscale, float* row_loss /*[rows+1]*/, float* loss /*1*/,
                          void* dlogits, cudaStream_t s);
 
+// GELU (erf) forward: out = gelu(pre); backward: out = dy * gelu'(pre).  One vectorised pass each (loss.cu).
+void launch_gelu(const void* pre, const void* dy, void* out, DType dt, size_t n, bool backward, cudaStream_t s);
+
 // ---------------- layer norm (layernorm.cu) -----------------------------------------------------
 void launch_layernorm_fwd(const void* x, const void* gamma, const void* beta, DType dt, int rows, int cols,
                           float eps, void* y, float* mean, float* rstd, cudaStream_t s);

@@ -52,7 +52,7 @@ class _LinearTC(torch.autograd.Function):
         if activation == "gelu":
             # keep the pre-activation for the backward (GELU' needs it): two launches, one extra tensor
             pre = C.gemm_nt(x2, weight, bias, EPI_BIAS, None)
-            y = F.gelu(pre)
+            y = C.gelu_fwd(pre)
             ctx.save_for_backward(x2, weight, pre)
         else:
             y = C.gemm_nt(x2, weight, bias, epi, None)
@@ -70,10 +70,7 @@ class _LinearTC(torch.autograd.Function):
         if ctx.activation == "relu":
             dy2 = dy2 * (aux > 0).to(dy2.dtype)
         elif ctx.activation == "gelu":
-            pre = aux.float()
-            cdf = 0.5 * (1.0 + torch.erf(pre * (1.0 / math.sqrt(2.0))))
-            pdf = torch.exp(-0.5 * pre * pre) * (1.0 / math.sqrt(2.0 * math.pi))
-            dy2 = (dy2.float() * (cdf + pre * pdf)).to(dy2.dtype)
+            dy2 = C.gelu_bwd(dy2.contiguous(), aux)          # dy * gelu'(pre) in one pass
         if not dy2.is_contiguous():
             dy2 = dy2.contiguous()
         dx = dw = db = None

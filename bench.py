@@ -505,7 +505,8 @@ def run_stock(args):
     is_bert = args.model.startswith("bert")
     if is_bert:
         from transformers import BertConfig, BertForMaskedLM
-        model = BertForMaskedLM(BertConfig(vocab_size=30528, attn_implementation="sdpa")).to(dev)
+        model = BertForMaskedLM(BertConfig(vocab_size=30528, attn_implementation="sdpa", hidden_dropout_prob=0.0,
+                                           attention_probs_dropout_prob=0.0)).to(dev)   # dropout off in both arms
     else:
         import torchvision
         model = getattr(torchvision.models, args.model)().to(dev).to(memory_format=torch.channels_last)
