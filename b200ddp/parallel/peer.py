@@ -172,9 +172,9 @@ class PeerCollectives:
             if scale != 1.0:
                 t.mul_(scale)
             return
-        off = getattr(t, "_b200_arena_off", None)
-        if off is None:
-            raise ValueError("allreduce_symmetric_ needs a tensor from symmetric_empty()")
+        off = t.data_ptr() - self.arena.local_ptr()          # slices / views of a symmetric tensor are symmetric too
+        if off < 0 or off + t.numel() * t.element_size() > self.arena.bytes() or not t.is_contiguous():
+            raise ValueError("allreduce_symmetric_ needs a contiguous tensor (or slice) from symmetric_empty()")
         self.C.allreduce_symmetric(self.arena, off, t.numel(), _DTYPE_CODE[t.dtype], _ALGO[algo], blocks or self.tail_blocks,
                                    scale, pad_set, self.timeout_s)
 
