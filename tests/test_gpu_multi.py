@@ -20,6 +20,10 @@ def _entry(rank, fn, world, port, args):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       LOCAL_RANK=str(rank), B200DDP_TIMEOUT_S="6")
     torch.cuda.set_device(rank)
+    if os.environ.get("B200DDP_TEST_DUMP_AFTER"):          # debugging aid: dump every rank's Python stack if a test stalls
+        import faulthandler
+        import sys
+        faulthandler.dump_traceback_later(float(os.environ["B200DDP_TEST_DUMP_AFTER"]), exit=True, file=sys.stderr)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         fn(rank, world, *args)
