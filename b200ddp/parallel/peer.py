@@ -80,6 +80,13 @@ class PeerCollectives:
         self.blocks = int(os.environ.get("B200DDP_COMM_BLOCKS", "24"))
         self.tail_blocks = int(os.environ.get("B200DDP_TAIL_BLOCKS", "96"))
         self.closed = False
+        if self.world > 1:
+            # device-side rendezvous with a generous budget: absorbs first-launch skew between ranks (lazy module
+            # loading, allocator warm-up) so the per-operation timeout only ever measures a peer that is really gone
+            self.C.peer_barrier(self.arena, 1, 0, 120.0)
+            torch.cuda.synchronize(self.device)
+            self.check()
+            self._host_barrier()
 
     # ---- bootstrap helpers --------------------------------------------------------------------
     def _host_barrier(self) -> None:

@@ -28,12 +28,16 @@ def _entry(rank, fn, world, port, args):
     try:
         fn(rank, world, *args)
         torch.cuda.synchronize()
+    except BaseException:
+        # a failing rank must not wait for its peers in collective teardown (they may be blocked on it): report and leave
+        import traceback
+        traceback.print_exc()
+        os._exit(1)
+    try:
+        from b200ddp.parallel.peer import PeerCollectives
+        PeerCollectives.shutdown_all()
     finally:
-        try:
-            from b200ddp.parallel.peer import PeerCollectives
-            PeerCollectives.shutdown_all()
-        finally:
-            dist.destroy_process_group()
+        dist.destroy_process_group()
 
 
 def _spawn(fn, port, *args, world=None):
