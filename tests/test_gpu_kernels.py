@@ -209,6 +209,9 @@ def test_bert_tiny_gpu_matches_cpu_reference():
     assert abs(float(lg) - float(lr)) < 5e-2 * max(1.0, abs(float(lr)))
     worst = 0.0
     for (n, p), q in zip(gpu.named_parameters(), ref.parameters()):
+        if float(q.grad.norm()) < 1e-4:      # e.g. key.bias: softmax is shift-invariant, its true gradient is exactly 0
+            assert float(p.grad.float().norm()) < 5e-2, n
+            continue
         rel = float((p.grad.float().cpu() - q.grad).norm() / (q.grad.norm() + 1e-8))
         worst = max(worst, rel)
         assert rel < 0.15, (n, rel)
