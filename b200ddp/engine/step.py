@@ -21,7 +21,7 @@ import torch
 class TrainStep:
     def __init__(self, model, criterion, optimizer, device: torch.device, accumulation: int = 1, use_graph: bool = False,
                  input_transform: Optional[Callable] = None, target_transform: Optional[Callable] = None,
-                 graph_warmup: int = 3):
+                 graph_warmup: int = 3, loss_scale: float = 1.0):
         self.model = model
         self.criterion = criterion
         self.optimizer = optimizer
@@ -31,6 +31,11 @@ class TrainStep:
         self.target_transform = target_transform
         self.use_graph = bool(use_graph) and self.device.type == "cuda" and self.accumulation == 1
         self.graph_warmup = graph_warmup
+        # static loss scaling (the reference's --loss_scale, ddp.py:179/307): the loss is multiplied before backward and the
+        # optimizer divides the gradients again inside the fused kernel (grad_scale); bf16 needs none, so the default is 1
+        self.loss_scale = float(loss_scale) if loss_scale and loss_scale > 0 else 1.0
+        if self.loss_scale != 1.0 and hasattr(optimizer, "grad_scale"):
+            optimizer.grad_scale = 1.0 / self.loss_scale
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self._static_x = self._static_y = self._static_loss = None
         self._graph_shapes = None
@@ -57,7 +62,7 @@ class TrainStep:
             loss = self.criterion(out, y)
             if self.accumulation > 1:
                 loss = loss / self.accumulation
-            loss.backward()
+            (loss * self.loss_scale if self.loss_scale != 1.0 else loss).backward()
         return loss.detach()
 
     def _apply_optimizer(self) -> None:

@@ -144,7 +144,8 @@ class Trainer:
             input_transform = self._make_image_transform()
         self.step_fn = TrainStep(model, self.criterion, self.optimizer, self.device,
                                  accumulation=args.gradient_accumulation_steps, use_graph=getattr(args, "cuda_graph", False),
-                                 input_transform=input_transform)
+                                 input_transform=input_transform,
+                                 loss_scale=float(getattr(args, "loss_scale", 0) or 0) if getattr(args, "fp16", False) else 1.0)
         self.global_step = 1
         self.tr_loss_host = 0.0
         self.timer = StepTimer(self.device, samples_per_step=args.train_batch_size * args.gradient_accumulation_steps * self._world())

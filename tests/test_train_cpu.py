@@ -113,3 +113,20 @@ def test_default_loss_and_dataset_per_model():
     assert tuple(x.shape) == (3, 224, 224) and y.dtype == torch.int64
     rn.loss = "mse"
     assert tuple(build_dataset(rn)[0][1].shape) == (1000,)
+
+
+def test_static_loss_scale_is_transparent():
+    """--loss_scale N multiplies the loss before backward and the fused optimizer divides the gradients again: the
+    trajectory is unchanged (up to rounding), clipping still sees unscaled gradients."""
+    from b200ddp.engine.step import TrainStep
+    torch.manual_seed(0)
+    a, b = FooModel(), FooModel()
+    b.load_state_dict(a.state_dict())
+    sa = TrainStep(a, MSELoss(), FusedSGD(a.parameters(), lr=0.1, max_grad_norm=0.5), torch.device("cpu"))
+    sb = TrainStep(b, MSELoss(), FusedSGD(b.parameters(), lr=0.1, max_grad_norm=0.5), torch.device("cpu"), loss_scale=1024.0)
+    for _ in range(5):
+        x, y = torch.randn(16, 10), torch.randn(16, 5)
+        la, lb = sa(x, y), sb(x, y)
+        assert torch.allclose(la, lb, atol=1e-6)
+    for p, q in zip(a.parameters(), b.parameters()):
+        assert torch.allclose(p, q, atol=1e-6)
