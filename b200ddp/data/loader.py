@@ -75,17 +75,16 @@ class BatchLoader:
             self._slots[slot] = cur
         return cur
 
-    def _index_batches(self) -> List[List[int]]:
-        out: List[List[int]] = []
+    def _index_batches(self) -> Iterator[List[int]]:
+        """Lazily group the sampler's indices into batches (the sampler may be endless, see ``EndlessSampler``)."""
         cur: List[int] = []
         for idx in self.sampler:
             cur.append(idx)
             if len(cur) == self.batch_size:
-                out.append(cur)
+                yield cur
                 cur = []
         if cur and not self.drop_last:
-            out.append(cur)
-        return out
+            yield cur
 
     def __iter__(self) -> Iterator[Tuple[torch.Tensor, ...]]:
         batches = self._index_batches()
@@ -97,23 +96,32 @@ class BatchLoader:
         # the GIL); batch k always lands in slot k % num_slots and is handed out in order.  A worker may run at most
         # `window` batches ahead of the consumer, so a slot is never refilled before its previous batch was taken
         # (and `_make` additionally waits for that batch's H2D copy to finish).
-        n = len(batches)
         window = max(1, self.num_slots - 3)
         cv = threading.Condition()
-        state = {"next": 0, "taken": 0, "stop": False, "err": None}
+        state = {"next": 0, "taken": 0, "stop": False, "err": None, "exhausted": False}
         ready = {}
 
         def work():
             while True:
                 with cv:
-                    while not state["stop"] and state["next"] < n and state["next"] >= state["taken"] + window:
+                    while not state["stop"] and not state["exhausted"] and state["next"] >= state["taken"] + window:
                         cv.wait(0.05)
-                    if state["stop"] or state["next"] >= n:
+                    if state["stop"] or state["exhausted"]:
+                        return
+                    try:
+                        idxs = next(batches)          # the index stream is shared: pulled under the lock, in order
+                    except StopIteration:
+                        state["exhausted"] = True
+                        cv.notify_all()
+                        return
+                    except BaseException as exc:
+                        state["err"] = exc
+                        cv.notify_all()
                         return
                     k = state["next"]
                     state["next"] += 1
                 try:
-                    item = self._make(batches[k], k % self.num_slots)
+                    item = self._make(idxs, k % self.num_slots)
                 except BaseException as exc:      # surface loader errors in the consumer
                     with cv:
                         state["err"] = exc
@@ -139,16 +147,20 @@ class BatchLoader:
         with _ACTIVE_LOCK:
             _ACTIVE.append(entry)
         try:
-            for k in range(n):
+            k = 0
+            while True:
                 with cv:
-                    while k not in ready and state["err"] is None:
+                    while k not in ready and state["err"] is None and not (state["exhausted"] and k >= state["next"]):
                         cv.wait(0.05)
                     if state["err"] is not None:
                         raise state["err"]
+                    if k not in ready:
+                        break                          # stream exhausted and every produced batch handed out
                     item = ready.pop(k)
                     state["taken"] = k + 1
                     cv.notify_all()
                 yield item
+                k += 1
         finally:
             with _ACTIVE_LOCK:
                 if entry in _ACTIVE:

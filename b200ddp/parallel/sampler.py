@@ -70,3 +70,28 @@ class ShardedSampler(torch.utils.data.Sampler):
 
     def __len__(self) -> int:
         return self.per_rank
+
+
+class EndlessSampler(torch.utils.data.Sampler):
+    """Chains epochs of a finite sampler into one endless index stream (``set_epoch`` is advanced on every pass), so a
+    loader's helper threads and prefetch queue never drain at an epoch boundary.  Meant for throughput runs over small
+    synthetic datasets where an "epoch" is only a handful of batches."""
+
+    def __init__(self, base, start_epoch: int = 0):
+        self.base = base
+        self.epoch = start_epoch
+
+    def __iter__(self):
+        while True:
+            if hasattr(self.base, "set_epoch"):
+                self.base.set_epoch(self.epoch)
+            n = 0
+            for idx in self.base:
+                n += 1
+                yield idx
+            if n == 0:
+                return
+            self.epoch += 1
+
+    def __len__(self) -> int:
+        return 1 << 62

@@ -180,7 +180,7 @@ def run_ours(args):
     from b200ddp.models import build_model
     from b200ddp.ops import CrossEntropyLoss, MSELoss
     from b200ddp.optim import FusedSGD, get_linear_schedule_with_warmup
-    from b200ddp.parallel import DistributedDataParallel, ShardedSampler
+    from b200ddp.parallel import DistributedDataParallel, EndlessSampler, ShardedSampler
     from b200ddp.utils import to_mixed_bf16
 
     rank, local_rank, world = dist_env()
@@ -242,17 +242,14 @@ def run_ours(args):
     dataset = make_dataset(args)
     sampler = ShardedSampler(dataset, num_replicas=world, rank=rank, shuffle=True, seed=0) if world > 1 else \
         torch.utils.data.RandomSampler(dataset)
-    loader = BatchLoader(dataset, batch_size=args.per_gpu_batch, sampler=sampler, drop_last=True, pin_memory=True)
+    # an endless index stream: with a small synthetic dataset sharded over 8 ranks an epoch is only 4 batches, and
+    # draining the prefetch pipeline at every epoch boundary would be an artefact of the benchmark, not of training
+    loader = BatchLoader(dataset, batch_size=args.per_gpu_batch, sampler=EndlessSampler(sampler), drop_last=True, pin_memory=True)
 
     def batches():
-        epoch = 0
-        while True:
-            if hasattr(sampler, "set_epoch"):
-                sampler.set_epoch(epoch)
-            feed = DevicePrefetcher(loader, dev)
-            for b in feed:
-                yield b, feed
-            epoch += 1
+        feed = DevicePrefetcher(loader, dev)
+        for b in feed:
+            yield b, feed
 
     stream = batches()
 

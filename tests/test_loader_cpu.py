@@ -44,3 +44,18 @@ def test_threaded_loader_surfaces_errors():
 
     with pytest.raises(ValueError, match="boom"):
         list(_threaded(Broken(64), batch_size=8))
+
+
+def test_endless_sampler_streams_across_epochs():
+    from b200ddp.parallel import EndlessSampler
+    ds = FooDataset(40)
+    base = ShardedSampler(ds, num_replicas=2, rank=0, seed=1)
+    loader = _threaded(ds, batch_size=8, sampler=EndlessSampler(base), drop_last=True)
+    expect = []
+    for epoch in range(3):
+        base.set_epoch(epoch)
+        expect += list(base)
+    it = iter(loader)
+    rows = torch.cat([next(it)[0] for _ in range(7)])     # 20 indices per epoch -> crosses two epoch boundaries
+    it.close()
+    assert torch.equal(rows, ds.X[torch.tensor(expect[:56])])
