@@ -254,7 +254,7 @@ size_t PeerArena::alloc(size_t nbytes, size_t align) {
   size_t off = round_up(bump_, align);
   if (off + nbytes > bytes_)
     throw std::runtime_error("PeerArena: out of symmetric memory (need " + std::to_string(off + nbytes) +
-                             " of " + std::to_string(bytes_) + " bytes); raise arena_mb");
+                             " of " + std::to_string(bytes_) + " bytes); set B200DDP_ARENA_MB to a larger arena");
   bump_ = off + nbytes;
   return off;
 }

@@ -181,6 +181,9 @@ class DistributedDataParallel(nn.Module):
         self._names = {id(p): n for n, p in module.named_parameters()}
         device = self._params[0].device
         self.backend_name = pick_backend_name(backend, device)
+        alone = not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(process_group) == 1
+        if self.backend_name == "b200" and alone:
+            self.backend_name = "single"           # nothing to reduce: no arena, no hooks
         if self.backend_name == "b200":
             from .peer import PeerCollectives
             grad_bytes = sum(p.numel() * max(4, p.element_size()) for p in self._params)
