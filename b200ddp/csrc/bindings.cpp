@@ -450,6 +450,13 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
      py::arg("epilogue") = 0, py::arg("out_fp32") = false, py::arg("out") = py::none());
   m.def("gemm_supported", &gemm_shape_supported);
   m.def("set_gemm_cta_mode", &set_gemm_cta_mode);
+  m.def("set_gemm_group_m", &set_gemm_group_m);
+  m.def("gemm_tile_order", [](int num_m, int num_n, int group_m) {
+    // host mirror of the device rasterisation: tile id -> (m block, n block)
+    std::vector<std::pair<int, int>> out((size_t)num_m * num_n);
+    for (int t = 0; t < num_m * num_n; ++t) gemm_tile_coords(t, num_m, num_n, group_m, &out[t].first, &out[t].second);
+    return out;
+  });
 
   // ---- fused BatchNorm ---------------------------------------------------------------------------
   m.def("bn_workspace", [](int R, int C) {

@@ -123,6 +123,7 @@ struct GemmParams {
   int epilogue;           // 0 none, 1 +bias, 2 +bias,relu, 3 +bias,gelu(erf)
   int out_fp32;
   int accumulate;         // D += result (fp32 output only; gradient accumulation)
+  int group_m;            // tile rasterisation, see gemm_tile_coords
   void* d;
   const __nv_bfloat16* bias;
 };
@@ -232,8 +233,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile % num_m_blocks) * BLOCK_M;
-        const int n0 = (tile / num_m_blocks) * BLOCK_N;
+        int mb, nb;
+        gemm_tile_coords(tile, num_m_blocks, num_n_blocks, p.group_m, &mb, &nb);
+        const int m0 = mb * BLOCK_M;
+        const int n0 = nb * BLOCK_N;
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::kStageBytes;
@@ -301,8 +304,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     int accum = 0;
     uint32_t accum_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile % num_m_blocks) * BLOCK_M;
-      const int n0 = (tile / num_m_blocks) * BLOCK_N;
+      int mb, nb;
+      gemm_tile_coords(tile, num_m_blocks, num_n_blocks, p.group_m, &mb, &nb);
+      const int m0 = mb * BLOCK_M;
+      const int n0 = nb * BLOCK_N;
       mbar_wait(&tmem_full_bar[accum], accum_phase);
       tc_fence_after();
       const int row = m0 + ew * 32 + lane;
@@ -419,8 +424,10 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-        const int m0 = (tile % num_m_blocks) * (2 * BLOCK_M) + (int)cta_rank * BLOCK_M;
-        const int n0 = (tile / num_m_blocks) * BN + (int)cta_rank * HALF_N;
+        int mb, nb;
+        gemm_tile_coords(tile, num_m_blocks, num_n_blocks, p.group_m, &mb, &nb);
+        const int m0 = mb * (2 * BLOCK_M) + (int)cta_rank * BLOCK_M;
+        const int n0 = nb * BN + (int)cta_rank * HALF_N;
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::kStageBytes;
@@ -486,8 +493,10 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     int accum = 0;
     uint32_t accum_phase = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-      const int m0 = (tile % num_m_blocks) * (2 * BLOCK_M) + (int)cta_rank * BLOCK_M;
-      const int n0 = (tile / num_m_blocks) * BN;
+      int mb, nb;
+      gemm_tile_coords(tile, num_m_blocks, num_n_blocks, p.group_m, &mb, &nb);
+      const int m0 = mb * (2 * BLOCK_M) + (int)cta_rank * BLOCK_M;
+      const int n0 = nb * BN;
       mbar_wait(&tmem_full_bar[accum], accum_phase);
       tc_fence_after();
       const int row = m0 + ew * 32 + lane;
@@ -593,10 +602,12 @@ void launch_variant_2cta(const void* a, const void* b, const GemmParams& p, cuda
 }
 
 int g_gemm_mode = -1;   // -1 auto, 1 force 1-CTA, 2 force 2-CTA (B200DDP_GEMM_CTAS)
+int g_gemm_group_m = -1;   // -1 = read B200DDP_GEMM_GROUP_M on first use
 
 }  // namespace
 
 void set_gemm_cta_mode(int mode) { g_gemm_mode = mode; }
+void set_gemm_group_m(int group_m) { g_gemm_group_m = group_m; }
 
 bool gemm_shape_supported(int M, int N, int K, bool a_mn, bool b_mn) {
   if (M < 1 || N < 1 || K < 1) return false;
@@ -622,6 +633,11 @@ void launch_gemm_bf16(const void* a, const void* b, void* d, const void* bias, i
     const char* e = getenv("B200DDP_GEMM_CTAS");
     g_gemm_mode = e ? atoi(e) : 0;
   }
+  if (g_gemm_group_m == -1) {
+    const char* e = getenv("B200DDP_GEMM_GROUP_M");
+    g_gemm_group_m = e ? atoi(e) : 0;
+  }
+  p.group_m = g_gemm_group_m > 0 ? g_gemm_group_m : 0;
   // Tile-shape choice by wave quantisation: cost = waves x per-tile work x a measured inefficiency factor of the
   // configuration (CTA pairs feed the tensor pipe best; 128x128 single-CTA tiles are shared-memory-bandwidth bound).
   auto waves = [](long long tiles, long long slots) { return (tiles + slots - 1) / slots; };

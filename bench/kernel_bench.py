@@ -95,6 +95,12 @@ def main():
                 C.set_gemm_cta_mode(mode)
                 ms = timeit(lambda: C.gemm(a, b, None, False, False, 0, False, out), args.iters)
                 record(f"gemm_nt[{tag}] {M}x{N}x{K}", ms, flops=2.0 * M * N * K, lib_ms=lib)
+                if mode == 2 and M >= 2048:
+                    for g in (4, 8, 16):       # grouped rasterisation (opt-in): L2 reuse of both operands
+                        C.set_gemm_group_m(g)
+                        ms = timeit(lambda: C.gemm(a, b, None, False, False, 0, False, out), args.iters)
+                        record(f"gemm_nt[{tag},group_m={g}] {M}x{N}x{K}", ms, flops=2.0 * M * N * K, lib_ms=lib)
+                    C.set_gemm_group_m(0)
             C.set_gemm_cta_mode(0)
         # backward layouts on the BERT FFN shape
         M, N, K = 16384, 3072, 768
