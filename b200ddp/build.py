@@ -68,7 +68,7 @@ def _flags():
     torch_lib = os.path.join(os.path.dirname(torch.__file__), "lib")
     link = [os.environ.get("CXX", "g++"), "-shared", "-o", str(ext_path())]
     libs = ["-L" + torch_lib, "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch", "-ltorch_python",
-            "-L" + os.path.join(cuda_home, "lib64"), "-lcudart", "-Wl,-rpath," + torch_lib, "-Wl,--no-as-needed"]
+            "-L" + os.path.join(cuda_home, "lib64"), "-lcudart", "-ldl", "-Wl,-rpath," + torch_lib, "-Wl,--no-as-needed"]
     return nvcc, cxx, link, libs
 
 

@@ -538,10 +538,14 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("normalize_to_channels_last", [](at::Tensor src, at::Tensor dst, at::Tensor mean, at::Tensor inv_std, double in_scale) {
     check_cuda(src, "src"); check_cuda(dst, "dst");
     TORCH_CHECK(src.dim() == 4 && src.is_contiguous(), "normalize_to_channels_last: src NCHW contiguous");
-    TORCH_CHECK(dst.is_contiguous(at::MemoryFormat::ChannelsLast) && dst.sizes() == src.sizes(), "normalize_to_channels_last: dst channels_last");
+    // dst may carry extra (zero-filled) channels: [N, C_out >= C, H, W]
+    TORCH_CHECK(dst.dim() == 4 && dst.is_contiguous(at::MemoryFormat::ChannelsLast) && dst.size(0) == src.size(0) &&
+                dst.size(1) >= src.size(1) && dst.size(2) == src.size(2) && dst.size(3) == src.size(3),
+                "normalize_to_channels_last: dst must be channels_last [N, C_out >= C, H, W]");
+    TORCH_CHECK(mean.numel() >= src.size(1) && inv_std.numel() >= src.size(1), "normalize_to_channels_last: mean/inv_std per source channel");
     c10::cuda::CUDAGuard guard(src.device());
     launch_normalize_to_channels_last(src.data_ptr(), dtype_of(src), dst.data_ptr(), dtype_of(dst), (int)src.size(0), (int)src.size(1),
-                                      (int)src.size(2), (int)src.size(3), mean.data_ptr<float>(), inv_std.data_ptr<float>(),
+                                      (int)dst.size(1), (int)src.size(2), (int)src.size(3), mean.data_ptr<float>(), inv_std.data_ptr<float>(),
                                       (float)in_scale, cur_stream());
   });
 }

@@ -84,8 +84,8 @@ void launch_maxpool3x3s2_bwd(const void* dy, const unsigned char* idx, void* dx,
 
 // ---------------- input pipeline (input.cu) -----------------------------------------------------
 // NCHW (u8 or fp32) -> NHWC-in-memory (channels_last) bf16/fp32 with per-channel (x*scale - mean)/std
-void launch_normalize_to_channels_last(const void* src, DType src_dt, void* dst, DType dst_dt, int n, int c, int h,
-                                       int w, const float* mean, const float* inv_std, float in_scale,
+void launch_normalize_to_channels_last(const void* src, DType src_dt, void* dst, DType dst_dt, int n, int c, int c_out,
+                                       int h, int w, const float* mean, const float* inv_std, float in_scale,
                                        cudaStream_t s);
 
 }  // namespace b200

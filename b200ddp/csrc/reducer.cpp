@@ -1,7 +1,10 @@
 #include "reducer.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <map>
+
+#include <nvtx3/nvToolsExt.h>   // header-only; a no-op unless a tool injected itself
 
 namespace b200 {
 
@@ -139,8 +142,23 @@ void Reducer::launch_in_order(cudaStream_t compute) {
   }
 }
 
+namespace {
+// B200DDP_NVTX=1: one range per bucket launch ("b200ddp.bucket<k> <bytes>B algo<a> x<blocks>") for timeline tools.
+bool nvtx_enabled() {
+  static const bool on = [] { const char* e = std::getenv("B200DDP_NVTX"); return e && std::atoi(e) != 0; }();
+  return on;
+}
+}  // namespace
+
 void Reducer::launch_bucket(int b, cudaStream_t compute) {
   BucketState& s = buckets_[b];
+  const bool mark = nvtx_enabled();
+  if (mark) {
+    const std::string label = "b200ddp.bucket" + std::to_string(b) + " " +
+                              std::to_string((long long)s.table.total_elems * (long long)dtype_size((DType)plans_[b].wire_dtype)) +
+                              "B algo" + std::to_string(s.algo) + " x" + std::to_string(s.blocks);
+    nvtxRangePushA(label.c_str());
+  }
   B200_CUDA_CHECK(cudaEventRecord(s.ready_event, compute));
   B200_CUDA_CHECK(cudaStreamWaitEvent(comm_stream_, s.ready_event, 0));
   float* sq = sq_partials_ ? sq_partials_ + (size_t)b * sq_stride_ : nullptr;
@@ -151,6 +169,7 @@ void Reducer::launch_bucket(int b, cudaStream_t compute) {
   launch_bucket_allreduce(ctx, s.table, s.stage_off, (DType)plans_[b].grad_dtype, (DType)plans_[b].wire_dtype, s.algo, s.blocks,
                           (opt_.as_view || opt_.find_unused) ? s.flat_out : nullptr, sq,
                           opt_.find_unused ? s.flags_dev : nullptr, scale, scatter, comm_stream_);
+  if (mark) nvtxRangePop();
   s.launched = true;
   ++launches;
   bytes_on_wire += (long long)s.table.total_elems * (long long)dtype_size((DType)plans_[b].wire_dtype);

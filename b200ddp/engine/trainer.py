@@ -161,17 +161,21 @@ class Trainer:
         inv_std = torch.ones(3, device=self.device)
         scratch = {}
         cl = bool(getattr(self.args, "channels_last", False))
+        inner = getattr(self.model, "module", self.model)
+        pad_c = int(getattr(inner, "input_channels", 0) or 0) if cl else 0
 
         def transform(x):
             if x.dim() != 4 or x.dtype not in (torch.float32, torch.uint8) or not x.is_contiguous():
                 return x
+            # the model may ask for zero-padded channels (ResNet stem, see models/resnet.py::input_channels)
+            shape = (x.shape[0], max(int(x.shape[1]), pad_c), x.shape[2], x.shape[3])
             dst = self.step_fn.static_inputs()[0]
-            if dst is None or dst.shape != x.shape or dst.dtype != self.compute_dtype:
-                dst = scratch.get(tuple(x.shape))
+            if dst is None or tuple(dst.shape) != shape or dst.dtype != self.compute_dtype:
+                dst = scratch.get(shape)
                 if dst is None:
-                    dst = torch.empty(x.shape, dtype=self.compute_dtype, device=self.device)
+                    dst = torch.empty(shape, dtype=self.compute_dtype, device=self.device)
                     dst = dst.contiguous(memory_format=torch.channels_last) if cl else dst
-                    scratch[tuple(x.shape)] = dst
+                    scratch[shape] = dst
             if not dst.is_contiguous(memory_format=torch.channels_last):
                 return x.to(self.compute_dtype)
             C.normalize_to_channels_last(x, dst, mean, inv_std, 1.0 / 255.0 if x.dtype == torch.uint8 else 1.0)

@@ -4,10 +4,12 @@ parameter order/shapes match torchvision's - bucket layouts quoted in SURVEY §2
 Convolutions / BatchNorm go to cuDNN through torch (not named hot ops in the north-star)."""
 from __future__ import annotations
 
+import os
 from typing import List
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from ..ops import FusedBatchNormAct2d, Linear, MaxPool3x3s2
 
@@ -34,8 +36,17 @@ class Bottleneck(nn.Module):
 
 
 class ResNet(nn.Module):
-    def __init__(self, layers: List[int], num_classes: int = 1000, zero_init_residual: bool = False):
+    def __init__(self, layers: List[int], num_classes: int = 1000, zero_init_residual: bool = False,
+                 stem_pad_to: int | None = None):
         super().__init__()
+        # Opt-in (B200DDP_STEM_PAD=8): feed the 7x7 stem an input with zero channels appended.  With C=3 the NHWC
+        # operand is not 16-byte aligned and cuDNN falls back to an sm80 TF32 kernel plus two layout-convert
+        # kernels (0.33 ms of a 5 ms step, profiles/launches_graph.md); C=8 is eligible for the sm_100 bf16
+        # kernels.  The parameter keeps torchvision's [64,3,7,7] shape (checkpoints unchanged); the zero taps
+        # are appended on the fly.
+        if stem_pad_to is None:
+            stem_pad_to = int(os.environ.get("B200DDP_STEM_PAD", "0") or 0)
+        self.stem_pad_to = stem_pad_to if stem_pad_to > 3 else 0
         self.inplanes = 64
         self.conv1 = nn.Conv2d(3, 64, 7, stride=2, padding=3, bias=False)
         self.bn1 = FusedBatchNormAct2d(64, relu=True)
@@ -67,16 +78,30 @@ class ResNet(nn.Module):
         mods += [Bottleneck(self.inplanes, planes) for _ in range(1, blocks)]
         return nn.Sequential(*mods)
 
+    @property
+    def input_channels(self) -> int:
+        """Channels the fused input kernel should emit (extra ones zero-filled)."""
+        return self.stem_pad_to or 3
+
+    def _stem(self, x):
+        if not self.stem_pad_to:
+            return self.conv1(x)
+        extra = self.stem_pad_to - self.conv1.weight.shape[1]
+        if x.shape[1] != self.stem_pad_to:            # caller did not pad (plain 3-channel batch)
+            x = F.pad(x, (0, 0, 0, 0, 0, self.stem_pad_to - x.shape[1]))
+        w = F.pad(self.conv1.weight, (0, 0, 0, 0, 0, extra))
+        return F.conv2d(x, w, None, self.conv1.stride, self.conv1.padding)
+
     def forward(self, x):
-        x = self.maxpool(self.bn1(self.conv1(x)))
+        x = self.maxpool(self.bn1(self._stem(x)))
         x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
         x = torch.flatten(self.avgpool(x), 1)
         return self.fc(x)
 
 
-def resnet50(num_classes: int = 1000) -> ResNet:
-    return ResNet([3, 4, 6, 3], num_classes)
+def resnet50(num_classes: int = 1000, **kw) -> ResNet:
+    return ResNet([3, 4, 6, 3], num_classes, **kw)
 
 
-def resnet152(num_classes: int = 1000) -> ResNet:
-    return ResNet([3, 8, 36, 3], num_classes)
+def resnet152(num_classes: int = 1000, **kw) -> ResNet:
+    return ResNet([3, 8, 36, 3], num_classes, **kw)

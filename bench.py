@@ -154,6 +154,18 @@ def make_dataset(args):
     return SyntheticTokens(samples=min(args.samples, 256))
 
 
+def opt_ins(model):
+    """Non-default kernel paths switched on through the environment (none by default) - recorded so a run is
+    reproducible from its JSON line."""
+    out = {}
+    if int(getattr(model, "stem_pad_to", 0) or 0):
+        out["stem_pad_channels"] = int(model.stem_pad_to)
+    for key in ("B200DDP_GEMM_GROUP_M", "B200DDP_GEMM_CTAS", "B200DDP_CONV1X1_TC", "B200DDP_BN_FUSED", "B200DDP_DISABLE_TC"):
+        if os.environ.get(key):
+            out[key] = os.environ[key]
+    return {"opt_in": out} if out else {}
+
+
 def config_dict(args, world, extra=None):
     cfg = {"model": args.model, "global_batch": args.per_gpu_batch * world, "per_gpu_batch": args.per_gpu_batch,
            "image_size": args.image_size if args.model.startswith("resnet") else None,
@@ -224,11 +236,13 @@ def run_ours(args):
     def input_transform(x):
         if not is_image:
             return x if x.dtype == compute_dtype or not x.is_floating_point() else x.to(compute_dtype)
+        # B200DDP_STEM_PAD (opt-in) makes the model ask for zero-padded input channels; default: same shape as x
+        shape = (x.shape[0], max(int(x.shape[1]), int(getattr(inner, "input_channels", 0) or 0)), x.shape[2], x.shape[3])
         buf = step.static_inputs()[0]          # after capture: write straight into the graph's input buffer
-        if buf is None or buf.shape != x.shape:
+        if buf is None or tuple(buf.shape) != shape:
             buf = static_in.get("x")
-        if buf is None or buf.shape != x.shape:
-            buf = torch.empty(x.shape, dtype=compute_dtype, device=dev).contiguous(memory_format=torch.channels_last)
+        if buf is None or tuple(buf.shape) != shape:
+            buf = torch.empty(shape, dtype=compute_dtype, device=dev).contiguous(memory_format=torch.channels_last)
             static_in["x"] = buf
         C.normalize_to_channels_last(x, buf, mean, inv_std, 1.0)
         return buf
@@ -345,7 +359,7 @@ def run_ours(args):
                "dtype": "bf16" if compute_dtype == torch.bfloat16 else "fp32",
                "data": "synthetic (random-init weights, random ImageNet-shaped batches in pinned host memory)",
                "config": config_dict(args, world, {"transport": backend, "cuda_graph": step.graph is not None,
-                                                   "ddp": stats}),
+                                                   "ddp": stats, **opt_ins(inner)}),
                "clocks": clocks, "gpu_launches": gpu_launches,
                "native_launches_per_step": per_step_graph if step.graph is not None else eager_launches / max(1, args.steps)}
         if e2e:

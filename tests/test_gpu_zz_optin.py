@@ -1,0 +1,36 @@
+"""Opt-in (default-off) paths prepared for measurement: zero-padded stem input, 1x1 convolutions on the tcgen05 GEMM.
+Sorted last on purpose: these paths are not in the default step."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_normalize_pads_channels_with_zeros():
+    from b200ddp import _ext
+    C = _ext.get()
+    x = torch.randn(4, 3, 32, 40, device="cuda")
+    mean = torch.tensor([0.1, 0.2, 0.3], device="cuda")
+    istd = torch.tensor([2.0, 0.5, 1.5], device="cuda")
+    dst = torch.full((4, 8, 32, 40), 7.0, device="cuda", dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    C.normalize_to_channels_last(x, dst, mean, istd, 1.0)
+    ref = ((x - mean.view(1, 3, 1, 1)) * istd.view(1, 3, 1, 1)).to(torch.bfloat16)
+    assert torch.allclose(dst[:, :3].float(), ref.float(), atol=1e-2, rtol=1e-2)
+    assert float(dst[:, 3:].abs().max()) == 0.0
+
+
+def test_resnet_padded_stem_matches_default_on_gpu():
+    from b200ddp.models.resnet import ResNet
+    from b200ddp.utils import to_mixed_bf16
+    torch.manual_seed(0)
+    a = to_mixed_bf16(ResNet([1, 1, 1, 1], num_classes=16).cuda()).to(memory_format=torch.channels_last)
+    b = to_mixed_bf16(ResNet([1, 1, 1, 1], num_classes=16, stem_pad_to=8).cuda()).to(memory_format=torch.channels_last)
+    b.load_state_dict(a.state_dict())
+    x = torch.randn(8, 3, 64, 64, device="cuda", dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    ya, yb = a(x), b(x)
+    assert float((ya.float() - yb.float()).norm() / ya.float().norm()) < 3e-2
+    ya.float().square().mean().backward()
+    yb.float().square().mean().backward()
+    ga, gb = a.conv1.weight.grad.float(), b.conv1.weight.grad.float()
+    assert gb.shape == ga.shape
+    assert float((ga - gb).norm() / ga.norm()) < 5e-2
