@@ -11,7 +11,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from ..ops import FusedBatchNormAct2d, Linear, MaxPool3x3s2
+from ..ops import FusedBatchNormAct2d, Linear, MaxPool3x3s2, PointwiseConv2d
 
 
 class Bottleneck(nn.Module):
@@ -20,11 +20,11 @@ class Bottleneck(nn.Module):
     def __init__(self, inplanes: int, planes: int, stride: int = 1, downsample: nn.Module | None = None):
         super().__init__()
         # BatchNorm + ReLU (and, for bn3, the shortcut add) are single fused kernels on channels_last CUDA tensors
-        self.conv1 = nn.Conv2d(inplanes, planes, 1, bias=False)
+        self.conv1 = PointwiseConv2d(inplanes, planes)
         self.bn1 = FusedBatchNormAct2d(planes, relu=True)
         self.conv2 = nn.Conv2d(planes, planes, 3, stride=stride, padding=1, bias=False)
         self.bn2 = FusedBatchNormAct2d(planes, relu=True)
-        self.conv3 = nn.Conv2d(planes, planes * self.expansion, 1, bias=False)
+        self.conv3 = PointwiseConv2d(planes, planes * self.expansion)
         self.bn3 = FusedBatchNormAct2d(planes * self.expansion, relu=True)
         self.downsample = downsample
 
@@ -71,7 +71,7 @@ class ResNet(nn.Module):
     def _make_layer(self, planes: int, blocks: int, stride: int) -> nn.Sequential:
         downsample = None
         if stride != 1 or self.inplanes != planes * Bottleneck.expansion:
-            downsample = nn.Sequential(nn.Conv2d(self.inplanes, planes * Bottleneck.expansion, 1, stride=stride, bias=False),
+            downsample = nn.Sequential(PointwiseConv2d(self.inplanes, planes * Bottleneck.expansion, stride=stride),
                                        FusedBatchNormAct2d(planes * Bottleneck.expansion))
         mods = [Bottleneck(self.inplanes, planes, stride, downsample)]
         self.inplanes = planes * Bottleneck.expansion

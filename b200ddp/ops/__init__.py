@@ -1,5 +1,5 @@
-from .functional import linear, mse_loss, cross_entropy, layer_norm
-from .modules import Linear, LayerNorm, MSELoss, CrossEntropyLoss
+from .functional import linear, conv1x1, mse_loss, cross_entropy, layer_norm
+from .modules import Linear, PointwiseConv2d, LayerNorm, MSELoss, CrossEntropyLoss
 from .batchnorm import FusedBatchNormAct2d, MaxPool3x3s2
 
-__all__ = ["linear", "mse_loss", "cross_entropy", "layer_norm", "Linear", "LayerNorm", "MSELoss", "CrossEntropyLoss", "FusedBatchNormAct2d", "MaxPool3x3s2"]
+__all__ = ["linear", "conv1x1", "PointwiseConv2d", "mse_loss", "cross_entropy", "layer_norm", "Linear", "LayerNorm", "MSELoss", "CrossEntropyLoss", "FusedBatchNormAct2d", "MaxPool3x3s2"]

@@ -130,6 +130,22 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     return y
 
 
+def conv1x1(x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    """Pointwise (1x1, stride 1, no bias) convolution of a channels_last activation as ONE tcgen05 GEMM:
+    the NHWC tensor *is* the row-major [N*H*W, C_in] operand, the [C_out, C_in, 1, 1] filter the [C_out, C_in]
+    one, and the [N*H*W, C_out] result is the channels_last output - no im2col, no copies.  dgrad / wgrad reuse
+    ``_LinearTC``'s MN-major GEMMs.  Two thirds of ResNet-50's convolutions have this shape."""
+    n, c, h, w = x.shape
+    co = weight.shape[0]
+    ok = (x.is_cuda and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and weight.shape[2:] == (1, 1)
+          and x.is_contiguous(memory_format=torch.channels_last) and _tc_ok(n * h * w, co, c))
+    if not ok:
+        return F.conv2d(x, weight)
+    x2 = x.permute(0, 2, 3, 1).reshape(n * h * w, c)            # view of the NHWC storage
+    y2 = _LinearTC.apply(x2, weight.reshape(co, c), None, None)
+    return y2.view(n, h, w, co).permute(0, 3, 1, 2)             # channels_last-strided [N, C_out, H, W]
+
+
 # ------------------------------------------------------------------------------------------------
 # Losses: forward computes loss AND input gradient in one launch
 # ------------------------------------------------------------------------------------------------

@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional
 
 import torch
@@ -33,6 +34,23 @@ class Linear(nn.Module):
 
     def extra_repr(self) -> str:
         return f"in={self.in_features}, out={self.out_features}, bias={self.bias is not None}, act={self.activation}"
+
+
+class PointwiseConv2d(nn.Conv2d):
+    """1x1 bias-free ``nn.Conv2d`` (same parameter name, shape and init).  Default: cuDNN, exactly like
+    ``nn.Conv2d``.  Opt-in (``B200DDP_CONV1X1_TC=1`` at construction, or ``use_tc=True``): stride-1 instances
+    run fprop / dgrad / wgrad on the tcgen05 GEMM (``functional.conv1x1``)."""
+
+    def __init__(self, in_channels: int, out_channels: int, stride: int = 1, use_tc: Optional[bool] = None, **kw):
+        super().__init__(in_channels, out_channels, 1, stride=stride, bias=False, **kw)
+        if use_tc is None:
+            use_tc = os.environ.get("B200DDP_CONV1X1_TC", "0") == "1"
+        self.use_tc = bool(use_tc) and self.stride == (1, 1)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self.use_tc and x.is_cuda:
+            return Fn.conv1x1(x, self.weight)
+        return super().forward(x)
 
 
 class LayerNorm(nn.Module):

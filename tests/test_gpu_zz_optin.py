@@ -34,3 +34,27 @@ def test_resnet_padded_stem_matches_default_on_gpu():
     ga, gb = a.conv1.weight.grad.float(), b.conv1.weight.grad.float()
     assert gb.shape == ga.shape
     assert float((ga - gb).norm() / ga.norm()) < 5e-2
+
+
+@pytest.mark.parametrize("shape", [(8, 64, 56, 56, 256), (4, 256, 14, 14, 64), (2, 512, 7, 7, 2048)])
+def test_conv1x1_on_tcgen05_matches_cudnn(shape):
+    from b200ddp.ops import PointwiseConv2d
+    n, ci, h, w, co = shape
+    torch.manual_seed(0)
+    ref = PointwiseConv2d(ci, co, use_tc=False).cuda().bfloat16().to(memory_format=torch.channels_last)
+    tc = PointwiseConv2d(ci, co, use_tc=True).cuda().bfloat16().to(memory_format=torch.channels_last)
+    tc.load_state_dict(ref.state_dict())
+    x = torch.randn(n, ci, h, w, device="cuda", dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    ya, yb = ref(xa), tc(xb)
+    assert yb.shape == ya.shape and yb.is_contiguous(memory_format=torch.channels_last)
+    g = torch.randn_like(ya)
+    ya.backward(g)
+    yb.backward(g)
+
+    def rel(a, b):
+        return float((a.float() - b.float()).norm() / (b.float().norm() + 1e-12))
+    assert rel(yb, ya) < 1e-2
+    assert rel(xb.grad, xa.grad) < 1e-2
+    assert tc.weight.grad.shape == ref.weight.grad.shape
+    assert rel(tc.weight.grad, ref.weight.grad) < 1e-2
