@@ -58,3 +58,25 @@ def test_conv1x1_on_tcgen05_matches_cudnn(shape):
     assert rel(xb.grad, xa.grad) < 1e-2
     assert tc.weight.grad.shape == ref.weight.grad.shape
     assert rel(tc.weight.grad, ref.weight.grad) < 1e-2
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="DataParallel needs two GPUs in one process")
+def test_data_parallel_matches_single_device():
+    """Reference ``ddp.py:189-191`` mode: one process, several GPUs.  Same loss and gradients as one device."""
+    from b200ddp.models import FooModel
+    from b200ddp.parallel import DataParallel
+    torch.manual_seed(0)
+    single = FooModel().cuda(0)
+    multi = FooModel().cuda(0)
+    multi.load_state_dict(single.state_dict())
+    dp = DataParallel(multi, device_ids=[0, 1])
+    x = torch.randn(64, 10, device="cuda:0")
+    y = torch.randn(64, 5, device="cuda:0")
+    la = torch.nn.functional.mse_loss(single(x), y)
+    lb = torch.nn.functional.mse_loss(dp(x), y)
+    la.backward()
+    lb.backward()
+    assert torch.allclose(la, lb, atol=1e-6)
+    for p, q in zip(single.parameters(), multi.parameters()):
+        assert torch.allclose(p.grad, q.grad, atol=1e-5)
+    assert set(dp.state_dict()) == set(single.state_dict())        # no "module." prefix in checkpoints
