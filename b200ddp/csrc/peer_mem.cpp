@@ -148,16 +148,25 @@ void PeerArena::exchange() {
   if (world_ > 1) {
     int fd = -1;
     B200_DRV_CHECK(drv.MemExportToShareableHandle(&fd, h, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0));
-    for (int r = 0; r < world_; ++r)
-      if (r != rank_) send_fd(r, fd, /*tag=*/0);
-    for (int got = 0; got < world_ - 1; ++got) {
-      int from = -1, tag = -1;
-      int pfd = recv_fd(&from, &tag);
-      if (from < 0 || from >= world_ || tag != 0) throw std::runtime_error("PeerArena: unexpected handle message");
-      CUmemGenericAllocationHandle ph;
-      B200_DRV_CHECK(drv.MemImportFromShareableHandle(&ph, (void*)(uintptr_t)pfd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR));
-      ::close(pfd);
-      peer_handles_[from] = ph;
+    try {
+      for (int r = 0; r < world_; ++r)
+        if (r != rank_) send_fd(r, fd, /*tag=*/0);
+      for (int got = 0; got < world_ - 1; ++got) {
+        int from = -1, tag = -1;
+        int pfd = recv_fd(&from, &tag);
+        if (from < 0 || from >= world_ || from == rank_ || tag != 0 || peer_handles_[from] != 0) {
+          ::close(pfd);
+          throw std::runtime_error("PeerArena: unexpected handle message");
+        }
+        CUmemGenericAllocationHandle ph;
+        const CUresult imported = drv.MemImportFromShareableHandle(&ph, (void*)(uintptr_t)pfd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR);
+        ::close(pfd);                       // the driver keeps its own reference; never leak the descriptor
+        B200_DRV_CHECK(imported);
+        peer_handles_[from] = ph;
+      }
+    } catch (...) {
+      ::close(fd);
+      throw;
     }
     ::close(fd);
   }
@@ -193,15 +202,24 @@ void PeerArena::multicast_create() {
     mc_handle_ = mh;
     int fd = -1;
     B200_DRV_CHECK(drv.MemExportToShareableHandle(&fd, mh, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0));
-    for (int r = 1; r < world_; ++r) send_fd(r, fd, /*tag=*/1);
+    try {
+      for (int r = 1; r < world_; ++r) send_fd(r, fd, /*tag=*/1);
+    } catch (...) {
+      ::close(fd);
+      throw;
+    }
     ::close(fd);
   } else {
     int from = -1, tag = -1;
     int fd = recv_fd(&from, &tag);
-    if (from != 0 || tag != 1) throw std::runtime_error("PeerArena: unexpected multicast message");
+    if (from != 0 || tag != 1) {
+      ::close(fd);
+      throw std::runtime_error("PeerArena: unexpected multicast message");
+    }
     CUmemGenericAllocationHandle mh;
-    B200_DRV_CHECK(drv.MemImportFromShareableHandle(&mh, (void*)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR));
+    const CUresult imported = drv.MemImportFromShareableHandle(&mh, (void*)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR);
     ::close(fd);
+    B200_DRV_CHECK(imported);
     mc_handle_ = mh;
   }
 }
