@@ -451,6 +451,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm_supported", &gemm_shape_supported);
   m.def("set_gemm_cta_mode", &set_gemm_cta_mode);
   m.def("set_gemm_group_m", &set_gemm_group_m);
+  m.def("set_gemm_tma_store", &set_gemm_tma_store);
   m.def("gemm_tile_order", [](int num_m, int num_n, int group_m) {
     // host mirror of the device rasterisation: tile id -> (m block, n block)
     std::vector<std::pair<int, int>> out((size_t)num_m * num_n);

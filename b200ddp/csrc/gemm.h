@@ -38,5 +38,7 @@ B200_HD inline void gemm_tile_coords(int tile, int num_m, int num_n, int group_m
 }
 // -1 = read B200DDP_GEMM_GROUP_M (default 0 = m-fastest)
 void set_gemm_group_m(int group_m);
+// -1 = read B200DDP_GEMM_TMA_STORE (default 0); 1 = bf16 outputs leave through shared memory + TMA stores
+void set_gemm_tma_store(int on);
 
 }  // namespace b200

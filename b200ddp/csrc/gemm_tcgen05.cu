@@ -128,24 +128,29 @@ struct GemmParams {
   const __nv_bfloat16* bias;
 };
 
+// bias / activation on 32 consecutive accumulator columns starting at `col0`
+__device__ __forceinline__ void epilogue_math(const GemmParams& p, int col0, const uint32_t* r, float* v) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+  if (p.epilogue >= 1 && p.bias != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (col0 + i < p.N) v[i] += __bfloat162float(p.bias[col0 + i]);
+  }
+  if (p.epilogue == 2) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+  } else if (p.epilogue == 3) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+  }
+}
+
 // Epilogue for one accumulator row chunk: 32 consecutive columns of row `row` starting at `col0`.
 __device__ __forceinline__ void store_row_chunk(const GemmParams& p, int row, int col0, const uint32_t* r) {
   if (row < p.M && col0 < p.N) {
     float v[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-    if (p.epilogue >= 1 && p.bias != nullptr) {
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (col0 + i < p.N) v[i] += __bfloat162float(p.bias[col0 + i]);
-    }
-    if (p.epilogue == 2) {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-    } else if (p.epilogue == 3) {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
-    }
+    epilogue_math(p, col0, r, v);
     const bool full = (col0 + 32 <= p.N);
     if (p.out_fp32) {
       float* out = reinterpret_cast<float*>(p.d) + (size_t)row * p.N + col0;
@@ -178,6 +183,64 @@ __device__ __forceinline__ void store_row_chunk(const GemmParams& p, int row, in
   }
 }
 
+// ---- opt-in epilogue through shared memory + TMA store (bf16 outputs) ---------------------------------------
+// Each epilogue warp owns two 4 KB staging buffers (32 rows x 64 bf16 columns, 128B-swizzled exactly like the
+// operand tiles).  A lane converts its accumulator row, writes eight 16-byte chunks at (chunk ^ (row & 7)) - bank
+// conflict free - and lane 0 hands the slab to the TMA unit, which writes full 128-byte rows and clips the M / N
+// edges.  The direct path instead issues 16-byte stores to 32 different rows per instruction.
+constexpr int kStoreSlabBytes = 32 * 64 * 2;                       // 4 KB
+constexpr int kStoreStageBytes = kNumEpilogueWarps * 2 * kStoreSlabBytes;   // 32 KB per CTA
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_le1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// One warp drains its 32 accumulator rows x TILE_N columns.  `row0` = global row of lane 0, `slab` = running slab
+// counter of this warp (selects the staging buffer; persists across tiles).
+template <int TILE_N>
+__device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUtensorMap* map_d, uint8_t* stage, uint32_t taddr,
+                                                  int row0, int n0, int lane, uint32_t& slab) {
+#pragma unroll 1
+  for (int c = 0; c < TILE_N; c += 64) {
+    if (n0 + c >= p.N) break;                       // warp-uniform: the rest of the tile is outside the matrix
+    uint8_t* buf = stage + (slab & 1u) * kStoreSlabBytes;
+    const uint32_t buf_s = smem_u32(buf);
+    // the store that used this buffer two slabs ago must have finished reading it
+    if (lane == 0) bulk_wait_read_le1();
+    __syncwarp();
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t r[32];
+      float v[32];
+      tmem_ld32(taddr + (uint32_t)(c + 32 * half), r);
+      tmem_ld_wait();
+      epilogue_math(p, n0 + c + 32 * half, r, v);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        __nv_bfloat162 h[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[8 * q + 2 * j], v[8 * q + 2 * j + 1]);
+        const int chunk = half * 4 + q;              // 16-byte chunk index inside the 128-byte row
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(h);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                     ::"r"(buf_s + (uint32_t)(lane * 128 + ((chunk ^ (lane & 7)) << 4))), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+      }
+    }
+    fence_async_smem();                              // generic-proxy writes -> visible to the TMA (async proxy)
+    __syncwarp();
+    if (lane == 0 && row0 < p.M) {
+      tma_store_2d(map_d, buf, n0 + c, row0);
+      bulk_commit();
+    }
+    ++slab;
+  }
+}
+
 template <int BLOCK_N, bool A_MN, bool B_MN>
 struct SmemLayout {
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
@@ -188,9 +251,10 @@ struct SmemLayout {
   static constexpr int kTotal = kStages * kStageBytes + kBarrierBytes + 1024 /*alignment slack*/;
 };
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
+template <int BLOCK_N, bool A_MN, bool B_MN, bool TMA_ST>
 __global__ void __launch_bounds__(kNumThreads, 1)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmParams p) {
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const __grid_constant__ CUtensorMap map_d, const GemmParams p) {
   using L = SmemLayout<BLOCK_N, A_MN, B_MN>;
   constexpr int kStages = L::kStages;
   constexpr uint32_t kTmemCols = kAccumStages * BLOCK_N;      // 256 or 512: power of two >= 32
@@ -303,6 +367,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int ew = warp - 4;                         // == warp % 4: this warp may touch TMEM lanes [32*ew, 32*ew+32)
     int accum = 0;
     uint32_t accum_phase = 0;
+    [[maybe_unused]] uint32_t slab = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int mb, nb;
       gemm_tile_coords(tile, num_m_blocks, num_n_blocks, p.group_m, &mb, &nb);
@@ -312,17 +377,25 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       tc_fence_after();
       const int row = m0 + ew * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(accum * BLOCK_N);
+      if constexpr (TMA_ST) {
+        epilogue_tile_tma<BLOCK_N>(p, &map_d, smem + kStages * L::kStageBytes + L::kBarrierBytes + ew * 2 * kStoreSlabBytes, taddr,
+                                   m0 + ew * 32, n0, lane, slab);
+      } else {
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 32) {
-        uint32_t r[32];
-        tmem_ld32(taddr + (uint32_t)c, r);
-        tmem_ld_wait();
-        store_row_chunk(p, row, n0 + c, r);
+        for (int c = 0; c < BLOCK_N; c += 32) {
+          uint32_t r[32];
+          tmem_ld32(taddr + (uint32_t)c, r);
+          tmem_ld_wait();
+          store_row_chunk(p, row, n0 + c, r);
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[accum]);     // this warp is done reading the accumulator
       if (++accum == kAccumStages) { accum = 0; accum_phase ^= 1; }
+    }
+    if constexpr (TMA_ST) {
+      if (lane == 0) bulk_wait_all();                         // staging smem must outlive the last store
     }
   }
 
@@ -378,9 +451,10 @@ struct SmemLayout2 {
   static constexpr int kTotal = kStages * kStageBytes + 1024 + 1024;
 };
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, bool TMA_ST>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
-gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmParams p) {
+gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                      const __grid_constant__ CUtensorMap map_d, const GemmParams p) {
   using L = SmemLayout2<A_MN, B_MN>;
   constexpr int BN = L::BN, HALF_N = BN / 2, kStages = L::kStages;
   constexpr uint32_t kTmemCols = kAccumStages * BN;   // 512
@@ -492,6 +566,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     const int ew = warp - 4;
     int accum = 0;
     uint32_t accum_phase = 0;
+    [[maybe_unused]] uint32_t slab = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       int mb, nb;
       gemm_tile_coords(tile, num_m_blocks, num_n_blocks, p.group_m, &mb, &nb);
@@ -501,17 +576,25 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       tc_fence_after();
       const int row = m0 + ew * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(accum * BN);
+      if constexpr (TMA_ST) {
+        epilogue_tile_tma<BN>(p, &map_d, smem + kStages * L::kStageBytes + 1024 + ew * 2 * kStoreSlabBytes, taddr, m0 + ew * 32, n0,
+                              lane, slab);
+      } else {
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t r[32];
-        tmem_ld32(taddr + (uint32_t)c, r);
-        tmem_ld_wait();
-        store_row_chunk(p, row, n0 + c, r);
+        for (int c = 0; c < BN; c += 32) {
+          uint32_t r[32];
+          tmem_ld32(taddr + (uint32_t)c, r);
+          tmem_ld_wait();
+          store_row_chunk(p, row, n0 + c, r);
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[accum]);
       if (++accum == kAccumStages) { accum = 0; accum_phase ^= 1; }
+    }
+    if constexpr (TMA_ST) {
+      if (lane == 0) bulk_wait_all();
     }
   }
 
@@ -566,48 +649,57 @@ CUtensorMap make_map(const void* ptr, int rows, int cols, int box_rows, int box_
   return map;
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
+// TMA_ST: epilogue through shared memory + TMA store (bf16 output, N % 8 == 0); the D map's box is one warp slab.
+template <int BLOCK_N, bool A_MN, bool B_MN, bool TMA_ST>
 void launch_variant(const void* a, const void* b, const GemmParams& p, cudaStream_t stream) {
   using L = SmemLayout<BLOCK_N, A_MN, B_MN>;
+  constexpr int kSmem = L::kTotal + (TMA_ST ? kStoreStageBytes : 0);
+  static_assert(kSmem <= 227 * 1024, "shared memory budget");
   // A: K-major stored [M,K] -> box {BLOCK_M rows, 64 cols};  MN-major stored [K,M] -> box {64 rows(k), 64 cols(m)}
   CUtensorMap map_a = A_MN ? make_map(a, p.K, p.M, BLOCK_K, 64) : make_map(a, p.M, p.K, BLOCK_M, BLOCK_K);
   CUtensorMap map_b = B_MN ? make_map(b, p.K, p.N, BLOCK_K, 64) : make_map(b, p.N, p.K, BLOCK_N, BLOCK_K);
-  auto kernel = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN>;
+  CUtensorMap map_d = TMA_ST ? make_map(p.d, p.M, p.N, 32, 64) : map_a;       // unused by the direct epilogue
+  auto kernel = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN, TMA_ST>;
   static bool configured = false;
   if (!configured) {
-    B200_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    B200_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     configured = true;
   }
   const int tiles = ceil_div(p.M, BLOCK_M) * ceil_div(p.N, BLOCK_N);
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-  kernel<<<grid, kNumThreads, L::kTotal, stream>>>(map_a, map_b, p);
+  kernel<<<grid, kNumThreads, kSmem, stream>>>(map_a, map_b, map_d, p);
   B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, bool TMA_ST>
 void launch_variant_2cta(const void* a, const void* b, const GemmParams& p, cudaStream_t stream) {
   using L = SmemLayout2<A_MN, B_MN>;
+  constexpr int kSmem = L::kTotal + (TMA_ST ? kStoreStageBytes : 0);
+  static_assert(kSmem <= 227 * 1024, "shared memory budget");
   CUtensorMap map_a = A_MN ? make_map(a, p.K, p.M, BLOCK_K, 64) : make_map(a, p.M, p.K, BLOCK_M, BLOCK_K);
   CUtensorMap map_b = B_MN ? make_map(b, p.K, p.N, BLOCK_K, 64) : make_map(b, p.N, p.K, L::BN / 2, BLOCK_K);
-  auto kernel = gemm_bf16_2cta_kernel<A_MN, B_MN>;
+  CUtensorMap map_d = TMA_ST ? make_map(p.d, p.M, p.N, 32, 64) : map_a;
+  auto kernel = gemm_bf16_2cta_kernel<A_MN, B_MN, TMA_ST>;
   static bool configured = false;
   if (!configured) {
-    B200_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    B200_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     configured = true;
   }
   const int tiles = ceil_div(p.M, 2 * BLOCK_M) * ceil_div(p.N, L::BN);
   const int pairs = tiles < kNumSMs / 2 ? tiles : kNumSMs / 2;
-  kernel<<<2 * pairs, kNumThreads, L::kTotal, stream>>>(map_a, map_b, p);     // __cluster_dims__(2,1,1) on the kernel
+  kernel<<<2 * pairs, kNumThreads, kSmem, stream>>>(map_a, map_b, map_d, p);     // __cluster_dims__(2,1,1) on the kernel
   B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
 }
 
 int g_gemm_mode = -1;   // -1 auto, 1 force 1-CTA, 2 force 2-CTA (B200DDP_GEMM_CTAS)
 int g_gemm_group_m = -1;   // -1 = read B200DDP_GEMM_GROUP_M on first use
+int g_gemm_tma_store = -1; // -1 = read B200DDP_GEMM_TMA_STORE on first use (default 0: direct register -> global epilogue)
 
 }  // namespace
 
 void set_gemm_cta_mode(int mode) { g_gemm_mode = mode; }
 void set_gemm_group_m(int group_m) { g_gemm_group_m = group_m; }
+void set_gemm_tma_store(int on) { g_gemm_tma_store = on; }
 
 bool gemm_shape_supported(int M, int N, int K, bool a_mn, bool b_mn) {
   if (M < 1 || N < 1 || K < 1) return false;
@@ -638,6 +730,12 @@ void launch_gemm_bf16(const void* a, const void* b, void* d, const void* bias, i
     g_gemm_group_m = e ? atoi(e) : 0;
   }
   p.group_m = g_gemm_group_m > 0 ? g_gemm_group_m : 0;
+  if (g_gemm_tma_store == -1) {
+    const char* e = getenv("B200DDP_GEMM_TMA_STORE");
+    g_gemm_tma_store = e ? atoi(e) : 0;
+  }
+  // staged epilogue: bf16 output with a TMA-legal row pitch, 16-byte aligned base, no read-modify-write
+  const bool tma_st = g_gemm_tma_store > 0 && !p.out_fp32 && !p.accumulate && N % 8 == 0 && (reinterpret_cast<uintptr_t>(d) & 15) == 0;
   // Tile-shape choice by wave quantisation: cost = waves x per-tile work x a measured inefficiency factor of the
   // configuration (CTA pairs feed the tensor pipe best; 128x128 single-CTA tiles are shared-memory-bandwidth bound).
   auto waves = [](long long tiles, long long slots) { return (tiles + slots - 1) / slots; };
@@ -655,9 +753,15 @@ void launch_gemm_bf16(const void* a, const void* b, void* d, const void* bias, i
   }
 #define B200_GEMM_DISPATCH(AMN, BMN)                                                   \
   if (a_mn == AMN && b_mn == BMN) {                                                    \
-    if (choice == 0) launch_variant_2cta<AMN, BMN>(a, b, p, stream);                   \
-    else if (choice == 1) launch_variant<256, AMN, BMN>(a, b, p, stream);              \
-    else launch_variant<128, AMN, BMN>(a, b, p, stream);                               \
+    if (tma_st) {                                                                      \
+      if (choice == 0) launch_variant_2cta<AMN, BMN, true>(a, b, p, stream);           \
+      else if (choice == 1) launch_variant<256, AMN, BMN, true>(a, b, p, stream);      \
+      else launch_variant<128, AMN, BMN, true>(a, b, p, stream);                       \
+    } else {                                                                           \
+      if (choice == 0) launch_variant_2cta<AMN, BMN, false>(a, b, p, stream);          \
+      else if (choice == 1) launch_variant<256, AMN, BMN, false>(a, b, p, stream);     \
+      else launch_variant<128, AMN, BMN, false>(a, b, p, stream);                      \
+    }                                                                                  \
     return;                                                                            \
   }
   B200_GEMM_DISPATCH(false, false)

@@ -83,7 +83,9 @@ def main():
 
     if "gemm" in want:
         shapes = [(8192, 8192, 8192), (16384, 768, 768), (16384, 3072, 768), (16384, 768, 3072), (16384, 2304, 768),
-                  (4096, 30528, 768), (32, 1000, 2048)]
+                  (4096, 30528, 768), (32, 1000, 2048),
+                  # ResNet-50 1x1 convolutions at batch 32 as GEMMs [N*H*W, C_out, C_in] (memory-bound: the epilogue matters)
+                  (100352, 256, 64), (100352, 64, 256), (25088, 512, 128), (6272, 1024, 256), (1568, 2048, 512)]
         for M, N, K in shapes:
             a = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
             b = torch.randn(N, K, device=dev, dtype=torch.bfloat16)
@@ -101,6 +103,10 @@ def main():
                         ms = timeit(lambda: C.gemm(a, b, None, False, False, 0, False, out), args.iters)
                         record(f"gemm_nt[{tag},group_m={g}] {M}x{N}x{K}", ms, flops=2.0 * M * N * K, lib_ms=lib)
                     C.set_gemm_group_m(0)
+                C.set_gemm_tma_store(1)            # staged epilogue (opt-in): smem + TMA store
+                ms = timeit(lambda: C.gemm(a, b, None, False, False, 0, False, out), args.iters)
+                record(f"gemm_nt[{tag},tma_store] {M}x{N}x{K}", ms, flops=2.0 * M * N * K, lib_ms=lib)
+                C.set_gemm_tma_store(0)
             C.set_gemm_cta_mode(0)
         # backward layouts on the BERT FFN shape
         M, N, K = 16384, 3072, 768

@@ -24,10 +24,11 @@ run base A=0
 run base_again A=0
 run stem_pad8 B200DDP_STEM_PAD=8
 run conv1x1_tc B200DDP_CONV1X1_TC=1
+run conv1x1_tc_tmastore B200DDP_CONV1X1_TC=1 B200DDP_GEMM_TMA_STORE=1
 run conv1x1_tc_group8 B200DDP_CONV1X1_TC=1 B200DDP_GEMM_GROUP_M=8
 run stem_pad8_conv1x1 B200DDP_STEM_PAD=8 B200DDP_CONV1X1_TC=1
 run bn_fused B200DDP_BN_FUSED=1
-echo "== GEMM rasterisation sweep"; timeout 600 python bench/kernel_bench.py --only gemm --out $O/kernels_groupm.json > $O/kernels_groupm.log 2>&1; echo "rc=$?"; grep -i "8192x8192x8192\|30528\|group" $O/kernels_groupm.log
+echo "== GEMM rasterisation sweep"; timeout 600 python bench/kernel_bench.py --only gemm --out $O/kernels_groupm.json > $O/kernels_groupm.log 2>&1; echo "rc=$?"; grep -i "gemm" $O/kernels_groupm.log
 echo "== launch list with the opt-ins on (who replaced whom)"
 B200DDP_STEM_PAD=8 B200DDP_CONV1X1_TC=1 timeout 400 ncu --clock-control none --cache-control none --metrics gpu__time_duration.sum \
     --profile-from-start off --csv --log-file $O/launches_optin.csv python bench.py --steps 2 --warmup 6 --skip_e2e --profile_range \
