@@ -1,9 +1,12 @@
 """Opt-in (default-off) paths prepared for measurement: zero-padded stem input, 1x1 convolutions on the tcgen05 GEMM.
 Sorted last on purpose: these paths are not in the default step."""
+import os
+
 import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
+unvalidated = pytest.mark.skipif(os.environ.get("B200DDP_TEST_OPTIN") != "1", reason="opt-in path not yet validated on a GPU; set B200DDP_TEST_OPTIN=1")
 
 
 def test_normalize_pads_channels_with_zeros():
@@ -36,6 +39,7 @@ def test_resnet_padded_stem_matches_default_on_gpu():
     assert float((ga - gb).norm() / ga.norm()) < 5e-2
 
 
+@unvalidated
 @pytest.mark.parametrize("shape", [(8, 64, 56, 56, 256), (4, 256, 14, 14, 64), (2, 512, 7, 7, 2048)])
 def test_conv1x1_on_tcgen05_matches_cudnn(shape):
     from b200ddp.ops import PointwiseConv2d

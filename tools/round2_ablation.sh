@@ -6,7 +6,7 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 O=gpurun_out
 B="python bench.py --gpus 1 --steps 60 --warmup 10 --skip_e2e"
-echo "== opt-in tests"; timeout 600 python -m pytest tests/test_gpu_zz_optin.py tests/test_gpu_zz_gemm_raster.py -m gpu -q > $O/test_optin.log 2>&1; echo "rc=$?"; tail -n 5 $O/test_optin.log
+echo "== opt-in tests"; B200DDP_TEST_OPTIN=1 timeout 600 python -m pytest tests/test_gpu_zz_optin.py tests/test_gpu_zz_gemm_raster.py -m gpu -q > $O/test_optin.log 2>&1; echo "rc=$?"; tail -n 5 $O/test_optin.log
 run() {  # name, env...
   local name=$1; shift
   echo "== $name"
