@@ -127,5 +127,41 @@ class BertForMaskedLM(nn.Module):
         return linear(h, self.bert.embeddings.word_embeddings.weight, self.decoder_bias)
 
 
+    # ---- interchange with the stock (Hugging Face) parameter naming ---------------------------------------
+    _LAYER_MAP = (("attention.self.query", "query"), ("attention.self.key", "key"), ("attention.self.value", "value"),
+                  ("attention.output.dense", "attn_out"), ("attention.output.LayerNorm", "attn_norm"),
+                  ("intermediate.dense", "ffn_in"), ("output.dense", "ffn_out"), ("output.LayerNorm", "ffn_norm"))
+
+    def load_hf_state_dict(self, hf: dict) -> None:
+        """Load a ``transformers.BertForMaskedLM`` state dict (the model the stock arm of ``bench.py`` trains), so a
+        checkpoint of the stock model continues on this one.  Vocabulary rows beyond the checkpoint's (padding up
+        to a multiple of ``pad_vocab_to``) are zero and their logits get a -inf-like bias so they never win."""
+        c = self.bert.config
+        own = self.state_dict()
+        out = {}
+
+        def put(dst, src):
+            t = hf[src]
+            if own[dst].shape != t.shape:                         # padded vocabulary
+                full = torch.zeros_like(own[dst])
+                if dst == "decoder_bias":
+                    full.fill_(-1e4)
+                full[:t.shape[0]] = t
+                t = full
+            out[dst] = t.to(own[dst].dtype)
+
+        for n in ("word_embeddings", "position_embeddings", "token_type_embeddings"):
+            put(f"bert.embeddings.{n}.weight", f"bert.embeddings.{n}.weight")
+        for wb in ("weight", "bias"):
+            put(f"bert.embeddings.LayerNorm.{wb}", f"bert.embeddings.LayerNorm.{wb}")
+            for i in range(c.layers):
+                for src, dst in self._LAYER_MAP:
+                    put(f"bert.encoder.{i}.{dst}.{wb}", f"bert.encoder.layer.{i}.{src}.{wb}")
+            put(f"transform.{wb}", f"cls.predictions.transform.dense.{wb}")
+            put(f"transform_norm.{wb}", f"cls.predictions.transform.LayerNorm.{wb}")
+        put("decoder_bias", "cls.predictions.bias")
+        self.load_state_dict(out, strict=True)
+
+
 def bert_base(with_mlm_head: bool = True) -> nn.Module:
     return BertForMaskedLM() if with_mlm_head else BertModel()

@@ -150,3 +150,47 @@ def test_resnet_stem_channel_padding_is_transparent():
     yb.square().mean().backward()
     assert torch.allclose(a.conv1.weight.grad, b.conv1.weight.grad, atol=1e-6)
     assert b.conv1.weight.grad.shape == (64, 3, 7, 7)
+
+
+def test_bert_matches_huggingface_reference_given_its_weights():
+    """Architecture parity with the stock model of the BERT config: same weights -> same logits (fp32, CPU)."""
+    import torch
+    transformers = pytest.importorskip("transformers")
+    from b200ddp.models.bert import BertConfig, BertForMaskedLM
+    torch.manual_seed(0)
+    hf_cfg = transformers.BertConfig(vocab_size=120, hidden_size=64, num_hidden_layers=2, num_attention_heads=4,
+                                     intermediate_size=128, max_position_embeddings=32, hidden_dropout_prob=0.0,
+                                     attention_probs_dropout_prob=0.0)
+    hf = transformers.BertForMaskedLM(hf_cfg).eval()
+    mine = BertForMaskedLM(BertConfig(vocab_size=120, hidden=64, layers=2, heads=4, intermediate=128, max_position=32,
+                                      pad_vocab_to=64)).eval()
+    mine.load_hf_state_dict(hf.state_dict())
+    ids = torch.randint(0, 120, (3, 17))
+    types = torch.randint(0, 2, (3, 17))
+    with torch.no_grad():
+        ref = hf(input_ids=ids, token_type_ids=types).logits
+        out = mine(ids, types)
+    assert out.shape == (3, 17, 128)                      # vocabulary padded to a multiple of 64
+    assert torch.allclose(out[..., :120], ref, atol=2e-4, rtol=1e-4)
+    assert float(out[..., 120:].max()) < -1e3             # padding logits can never win
+
+
+def test_resnet50_matches_torchvision_given_its_weights():
+    """Same parameter names / shapes as torchvision's ResNet-50 and the same function (train and eval mode)."""
+    import torch
+    tv = pytest.importorskip("torchvision")
+    from b200ddp.models import resnet50
+    torch.manual_seed(0)
+    ref = tv.models.resnet50(num_classes=10)
+    mine = resnet50(num_classes=10)
+    mine.load_state_dict(ref.state_dict())                 # strict: identical keys and shapes
+    x = torch.randn(2, 3, 64, 64)
+    for mode in ("eval", "train"):
+        getattr(ref, mode)()
+        getattr(mine, mode)()
+        with torch.no_grad():
+            a, b = ref(x), mine(x)
+        assert torch.allclose(a, b, atol=1e-4, rtol=1e-4), mode
+    # running statistics were updated identically by the training-mode pass
+    for (k, u), (_, v) in zip(ref.state_dict().items(), mine.state_dict().items()):
+        assert torch.allclose(u.float(), v.float(), atol=1e-5), k
