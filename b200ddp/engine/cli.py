@@ -63,6 +63,10 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--no_tensorboard", action="store_true")
     p.add_argument("--tb_dir", type=str, default=None)
     p.add_argument("--eval_at_end", action="store_true")
+    p.add_argument("--trace_dir", type=str, default=None,
+                   help="write a torch.profiler chrome trace (trace_rank<r>.json) of --trace_steps optimizer steps here")
+    p.add_argument("--trace_steps", type=int, default=3)
+    p.add_argument("--trace_skip", type=int, default=10, help="optimizer steps to skip before tracing (warm-up, graph capture)")
     return p
 
 

@@ -213,6 +213,9 @@ class Trainer:
         self.optimizer.zero_grad(set_to_none=True)
         t_start = time.time()
         done = False
+        tracer = self._make_tracer()
+        if self.device.type == "cuda":
+            torch.cuda.reset_peak_memory_stats(self.device)
         for epoch in trange(start_epoch, int(args.num_train_epochs), desc="Epoch", disable=not self.show_bars, leave=False):
             if self.distributed:
                 self.sampler.set_epoch(epoch)
@@ -234,6 +237,8 @@ class Trainer:
                     self.scheduler.step()
                     self.global_step += 1
                     self.timer.tick()
+                    if tracer is not None:
+                        tracer.step()
 
                     if args.logging_steps > 0 and self.global_step % args.logging_steps == 0:
                         total = self.step_fn.read_loss_sum() + self.tr_loss_host   # the only host sync, every logging_steps
@@ -261,7 +266,11 @@ class Trainer:
                 break
         total_loss = self.step_fn.read_loss_sum() + self.tr_loss_host
         elapsed = time.time() - t_start
+        if tracer is not None:
+            tracer.stop()
         extra = {}
+        if self.device.type == "cuda":
+            extra["peak_mem_gb"] = round(torch.cuda.max_memory_allocated(self.device) / 2 ** 30, 3)
         if self.last_throughput:
             extra = {"ms_per_step": round(self.last_throughput["ms_per_step"], 4),
                      "samples_per_s": round(self.last_throughput.get("samples_per_s", 0.0), 1)}
@@ -273,6 +282,30 @@ class Trainer:
             self.tb_writer.flush()
             self.tb_writer.close()
         return self.global_step, total_loss / self.global_step
+
+    # ------------------------------------------------------------------------------------------
+    def _make_tracer(self):
+        """``--trace_dir``: torch.profiler timeline (CPU ops, CUDA kernels, the NVTX-style ranges of ``nvtx_range``) of a
+        few optimizer steps per rank.  The reference has no tracing at all; numbers are never taken from a
+        traced run (``StepTimer`` reports the untraced steps)."""
+        trace_dir = getattr(self.args, "trace_dir", None)
+        steps = int(getattr(self.args, "trace_steps", 0) or 0)
+        if not trace_dir or steps <= 0:
+            return None
+        from torch.profiler import ProfilerActivity, profile, schedule
+        os.makedirs(trace_dir, exist_ok=True)
+        rank = dist.get_rank() if self.distributed else 0
+        path = os.path.join(trace_dir, f"trace_rank{rank}.json")
+        acts = [ProfilerActivity.CPU] + ([ProfilerActivity.CUDA] if self.device.type == "cuda" else [])
+
+        def on_ready(prof):
+            prof.export_chrome_trace(path)
+            self.log.info("Wrote profiler trace.", dict(path=path, steps=steps))
+
+        prof = profile(activities=acts, schedule=schedule(wait=int(getattr(self.args, "trace_skip", 10)), warmup=1, active=steps, repeat=1),
+                       on_trace_ready=on_ready)
+        prof.start()
+        return prof
 
     # ------------------------------------------------------------------------------------------
     def save(self, epoch: int, batches_in_epoch: int) -> Optional[str]:

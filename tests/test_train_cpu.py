@@ -194,3 +194,14 @@ def test_resnet50_matches_torchvision_given_its_weights():
     # running statistics were updated identically by the training-mode pass
     for (k, u), (_, v) in zip(ref.state_dict().items(), mine.state_dict().items()):
         assert torch.allclose(u.float(), v.float(), atol=1e-5), k
+
+
+def test_trace_dir_writes_a_chrome_trace(tmp_path):
+    """--trace_dir: a torch.profiler timeline of a few optimizer steps (the reference has no tracing)."""
+    import json
+    trace_dir = tmp_path / "traces"
+    _run(tmp_path, "--max_steps", "12", "--save_steps", "0", "--trace_dir", str(trace_dir), "--trace_steps", "2", "--trace_skip", "3")
+    path = trace_dir / "trace_rank0.json"
+    assert path.exists()
+    events = json.loads(path.read_text())["traceEvents"]
+    assert any("ProfilerStep" in str(e.get("name", "")) for e in events)
