@@ -15,6 +15,7 @@ path is the only one with native kernels.
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -81,15 +82,25 @@ class TorchCollectives:
             dist.barrier(group=self.group)
 
 
-def pick_backend_name(requested: str, device: torch.device) -> str:
-    """Resolve ``auto``: b200 on CUDA when the native extension + peer access are usable,
-    otherwise the process group's own backend."""
+def spans_one_nvswitch_domain(group=None) -> bool:
+    """True when every rank of ``group`` can sit in one peer-memory arena: <= 8 ranks, all on this host
+    (torchrun exports LOCAL_WORLD_SIZE; without a launcher there is only one process anyway)."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return True
+    world = dist.get_world_size(group)
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+    return world <= 8 and local_world >= world
+
+
+def pick_backend_name(requested: str, device: torch.device, group=None) -> str:
+    """Resolve ``auto``: b200 on CUDA when the native extension is usable and the job fits one NVSwitch domain,
+    otherwise the process group's own backend (multi-node jobs launched by ``run.sbatch`` reduce over NCCL)."""
     if requested != "auto":
         return requested
     if device.type == "cuda":
         try:
             from .. import _ext
-            if _ext.available():
+            if _ext.available() and spans_one_nvswitch_domain(group):
                 return "b200"
         except Exception:
             pass

@@ -180,7 +180,7 @@ class DistributedDataParallel(nn.Module):
             raise RuntimeError("DistributedDataParallel needs at least one parameter that requires grad")
         self._names = {id(p): n for n, p in module.named_parameters()}
         device = self._params[0].device
-        self.backend_name = pick_backend_name(backend, device)
+        self.backend_name = pick_backend_name(backend, device, process_group)
         alone = not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(process_group) == 1
         if self.backend_name == "b200" and alone:
             self.backend_name = "single"           # nothing to reduce: no arena, no hooks

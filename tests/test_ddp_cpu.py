@@ -150,3 +150,33 @@ def test_single_process_wrap_is_transparent():
     nn.functional.mse_loss(ddp(x), y).backward()
     assert all(p.grad is not None for p in model.parameters())
     assert list(ddp.state_dict().keys()) == ["net1.weight", "net1.bias", "net2.weight", "net2.bias"]
+
+
+def test_auto_backend_leaves_the_peer_transport_for_multi_node_jobs(monkeypatch):
+    """One peer-memory arena spans one NVSwitch domain (<= 8 GPUs of one host); `auto` must not pick it beyond that."""
+    from b200ddp.parallel import backend as B
+
+    class FakeDist:
+        def __init__(self, world):
+            self.world = world
+
+        def is_available(self):
+            return True
+
+        def is_initialized(self):
+            return True
+
+        def get_world_size(self, group=None):
+            return self.world
+
+    monkeypatch.setattr(B, "dist", FakeDist(8))
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "8")
+    assert B.spans_one_nvswitch_domain()
+    monkeypatch.setattr(B, "dist", FakeDist(16))            # 2 nodes x 8 (run.sbatch)
+    assert not B.spans_one_nvswitch_domain()
+    monkeypatch.setattr(B, "dist", FakeDist(8))             # 2 nodes x 4
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "4")
+    assert not B.spans_one_nvswitch_domain()
+    assert B.pick_backend_name("auto", torch.device("cuda", 0)) == "nccl"
+    assert B.pick_backend_name("b200", torch.device("cuda", 0)) == "b200"      # explicit choice is honoured
+    assert B.pick_backend_name("auto", torch.device("cpu")) == "gloo"
