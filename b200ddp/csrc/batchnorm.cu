@@ -505,6 +505,51 @@ bool fused_tile(int R, int C, Tile* t) {
 
 }  // namespace
 
+// Statistics from partial sums produced elsewhere ([2][G][C]: per-row-group column sums / sums of squares written by
+// the tcgen05 GEMM epilogue of the producing 1x1 convolution): 32 channels per block, 32 row-lanes per channel, fixed
+// summation order -> deterministic.  Same outputs as the finish step of bn_stats_kernel.
+__global__ void __launch_bounds__(1024) bn_finish_partials_kernel(const float* __restrict__ partial, int G, int C, int R,
+                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                  float* __restrict__ running_mean, float* __restrict__ running_var,
+                                                                  long long* __restrict__ num_batches, float* __restrict__ save_mean,
+                                                                  float* __restrict__ save_rstd, float* __restrict__ scale,
+                                                                  float* __restrict__ shift, float eps, float momentum) {
+  __shared__ float ssum[32][33], ssq[32][33];
+  const int tx = threadIdx.x & 31, l = threadIdx.x >> 5;
+  const int ch = blockIdx.x * 32 + tx;
+  float ps = 0.f, pq = 0.f;
+  if (ch < C) {
+#pragma unroll 4
+    for (int k = l; k < G; k += 32) {
+      ps += __ldcg(&partial[(size_t)k * C + ch]);
+      pq += __ldcg(&partial[((size_t)G + k) * C + ch]);
+    }
+  }
+  ssum[l][tx] = ps;
+  ssq[l][tx] = pq;
+  __syncthreads();
+  if (l == 0 && ch < C) {
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { s += ssum[i][tx]; q += ssq[i][tx]; }
+    const float inv_r = 1.f / (float)R;
+    const float mean = s * inv_r;
+    const float var = fmaxf(q * inv_r - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    const float sc = gamma[ch] * rstd;
+    save_mean[ch] = mean;
+    save_rstd[ch] = rstd;
+    scale[ch] = sc;
+    shift[ch] = beta[ch] - mean * sc;
+    if (running_mean != nullptr) {
+      const float unbiased = R > 1 ? var * ((float)R / (float)(R - 1)) : var;
+      running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * mean;
+      running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * unbiased;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && num_batches != nullptr) *num_batches += 1;
+}
+
 void bn_workspace_sizes(int R, int C, size_t* partial_floats, size_t* counters) {
   const Tile t = pick_tile(R, C);
   *partial_floats = (size_t)2 * t.grid_y * C;
@@ -530,6 +575,26 @@ void launch_bn_forward(const void* x, const void* residual, void* y, unsigned ch
 #undef B200_BN_FWD
   B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
   if (fused) return;
+  if (dt == DType::BF16)
+    bn_apply_kernel<__nv_bfloat16><<<apply_grid(t, R), kBnThreads, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)residual,
+                                                                           (__nv_bfloat16*)y, mask, scale, shift, R, C, t.cvb, t.ty, r);
+  else
+    bn_apply_kernel<float><<<apply_grid(t, R), kBnThreads, 0, s>>>((const float*)x, (const float*)residual, (float*)y, mask, scale, shift, R, C,
+                                                                   t.cvb, t.ty, r);
+  B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
+}
+
+void launch_bn_forward_from_partials(const void* x, const void* residual, void* y, unsigned char* mask, DType dt, int R, int C,
+                                     const float* gamma, const float* beta, float* running_mean, float* running_var,
+                                     long long* num_batches, float* save_mean, float* save_rstd, float* scale, float* shift,
+                                     const float* partial, int groups, float eps, float momentum, bool relu, cudaStream_t s) {
+  if (C % kVec != 0) throw std::runtime_error("fused batch norm: channel count must be a multiple of 8");
+  if (groups < 1) throw std::runtime_error("fused batch norm: empty partial statistics");
+  bn_finish_partials_kernel<<<(C + 31) / 32, 1024, 0, s>>>(partial, groups, C, R, gamma, beta, running_mean, running_var, num_batches,
+                                                         save_mean, save_rstd, scale, shift, eps, momentum);
+  B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
+  const Tile t = pick_tile(R, C);
+  const int r = relu ? 1 : 0;
   if (dt == DType::BF16)
     bn_apply_kernel<__nv_bfloat16><<<apply_grid(t, R), kBnThreads, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)residual,
                                                                            (__nv_bfloat16*)y, mask, scale, shift, R, C, t.cvb, t.ty, r);

@@ -448,6 +448,19 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     return d;
   }, py::arg("a"), py::arg("b"), py::arg("bias") = py::none(), py::arg("a_mn") = false, py::arg("b_mn") = false,
      py::arg("epilogue") = 0, py::arg("out_fp32") = false, py::arg("out") = py::none());
+  // forward GEMM (a [M,K], b [N,K]) that also returns per-32-row partial column statistics of its output: [2][ceil(M/32)][N]
+  m.def("gemm_stats", [](at::Tensor a, at::Tensor b) {
+    check_cuda(a, "a"); check_cuda(b, "b");
+    TORCH_CHECK(a.scalar_type() == at::kBFloat16 && b.scalar_type() == at::kBFloat16, "gemm_stats: bf16 operands");
+    TORCH_CHECK(a.dim() == 2 && b.dim() == 2 && a.is_contiguous() && b.is_contiguous() && a.size(1) == b.size(1), "gemm_stats: [M,K] x [N,K]");
+    c10::cuda::CUDAGuard guard(a.device());
+    const int M = (int)a.size(0), K = (int)a.size(1), N = (int)b.size(0);
+    at::Tensor d = at::empty({M, N}, a.options());
+    at::Tensor stats = at::empty({2, (M + 31) / 32, N}, a.options().dtype(at::kFloat));
+    launch_gemm_bf16(a.data_ptr(), b.data_ptr(), d.data_ptr(), nullptr, M, N, K, false, false, 0, DType::BF16, false, cur_stream(),
+                     stats.data_ptr<float>());
+    return std::make_tuple(d, stats);
+  });
   m.def("gemm_supported", &gemm_shape_supported);
   m.def("set_gemm_cta_mode", &set_gemm_cta_mode);
   m.def("set_gemm_group_m", &set_gemm_group_m);
@@ -491,6 +504,35 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
                       running_var.has_value() ? running_var->data_ptr<float>() : nullptr,
                       num_batches.has_value() ? (long long*)num_batches->data_ptr<int64_t>() : nullptr, st, st + C, st + 2 * C, st + 3 * C,
                       partial.data_ptr<float>(), (unsigned int*)counters.data_ptr<int>(), (float)eps, (float)momentum, relu, cur_stream());
+    return std::make_tuple(y, stats, mask);
+  });
+  m.def("bn_forward_partials", [](at::Tensor x, c10::optional<at::Tensor> residual, at::Tensor gamma, at::Tensor beta,
+                                  c10::optional<at::Tensor> running_mean, c10::optional<at::Tensor> running_var,
+                                  c10::optional<at::Tensor> num_batches, double eps, double momentum, bool relu, at::Tensor partial) {
+    check_cuda(x, "x"); check_cuda(partial, "partial");
+    TORCH_CHECK(x.dim() == 4 && x.is_contiguous(at::MemoryFormat::ChannelsLast), "bn_forward_partials: x must be 4-D channels_last");
+    TORCH_CHECK(gamma.scalar_type() == at::kFloat && beta.scalar_type() == at::kFloat, "bn_forward_partials: fp32 affine parameters");
+    const int C = (int)x.size(1);
+    const int R = (int)(x.numel() / C);
+    TORCH_CHECK(partial.scalar_type() == at::kFloat && partial.dim() == 3 && partial.size(0) == 2 && partial.size(2) == C &&
+                partial.is_contiguous(), "bn_forward_partials: partial statistics must be fp32 [2, groups, C]");
+    c10::cuda::CUDAGuard guard(x.device());
+    at::Tensor y = at::empty_like(x);
+    at::Tensor stats = at::empty({4, C}, x.options().dtype(at::kFloat));   // rows: save_mean, save_rstd, scale, shift
+    const void* res = nullptr;
+    if (residual.has_value()) {
+      TORCH_CHECK(residual->sizes() == x.sizes() && residual->dtype() == x.dtype() && residual->is_contiguous(at::MemoryFormat::ChannelsLast),
+                  "bn_forward_partials: residual must match x (shape, dtype, channels_last)");
+      res = residual->data_ptr();
+    }
+    float* st = stats.data_ptr<float>();
+    at::Tensor mask = relu ? at::empty({(int64_t)R, (int64_t)(C / 8)}, x.options().dtype(at::kByte)) : at::Tensor();
+    launch_bn_forward_from_partials(x.data_ptr(), res, y.data_ptr(), relu ? mask.data_ptr<uint8_t>() : nullptr, dtype_of(x), R, C,
+                                    gamma.data_ptr<float>(), beta.data_ptr<float>(),
+                                    running_mean.has_value() ? running_mean->data_ptr<float>() : nullptr,
+                                    running_var.has_value() ? running_var->data_ptr<float>() : nullptr,
+                                    num_batches.has_value() ? (long long*)num_batches->data_ptr<int64_t>() : nullptr, st, st + C, st + 2 * C,
+                                    st + 3 * C, partial.data_ptr<float>(), (int)partial.size(1), (float)eps, (float)momentum, relu, cur_stream());
     return std::make_tuple(y, stats, mask);
   });
   m.def("bn_backward", [](at::Tensor dy, at::Tensor x, c10::optional<at::Tensor> y, at::Tensor gamma, at::Tensor stats, bool relu,

@@ -14,8 +14,10 @@ namespace b200 {
 // D[M,N] = epi( sum_k A(m,k) * B(n,k) ).  a_mn=false: A stored [M,K]; a_mn=true: A stored [K,M].
 // b_mn=false: B stored [N,K]; b_mn=true: B stored [K,N].  All operands bf16 row-major, D bf16 or fp32.
 // epilogue: 0 none, 1 +bias[N], 2 +bias then ReLU, 3 +bias then GELU(erf).
+// col_stats (optional): fp32 workspace [2][ceil(M/32)][N]; the epilogue writes, per group of 32 output rows, the column sums
+// and sums of squares of the output as stored - BatchNorm statistics of a 1x1 convolution without re-reading its output.
 void launch_gemm_bf16(const void* a, const void* b, void* d, const void* bias, int M, int N, int K, bool a_mn, bool b_mn,
-                      int epilogue, DType out_dtype, bool accumulate, cudaStream_t stream);
+                      int epilogue, DType out_dtype, bool accumulate, cudaStream_t stream, float* col_stats = nullptr);
 void launch_gemm_nt_bf16(const void* a, const void* b, void* d, const void* bias, int M, int N, int K, int epilogue,
                          DType out_dtype, cudaStream_t stream);
 bool gemm_shape_supported(int M, int N, int K, bool a_mn, bool b_mn);

@@ -124,6 +124,8 @@ struct GemmParams {
   int out_fp32;
   int accumulate;         // D += result (fp32 output only; gradient accumulation)
   int group_m;            // tile rasterisation, see gemm_tile_coords
+  int stat_groups;        // ceil(M / 32): row groups of the column-statistics workspace
+  float* col_stats;       // [2][stat_groups][N] per-32-row partial column sums / sums of squares of the stored output, or nullptr
   void* d;
   const __nv_bfloat16* bias;
 };
@@ -143,6 +145,44 @@ __device__ __forceinline__ void epilogue_math(const GemmParams& p, int col0, con
   } else if (p.epilogue == 3) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+  }
+}
+
+// Column statistics of the producing GEMM (opt-in: BatchNorm statistics of a 1x1 convolution's output without
+// re-reading it).  A warp holds a 32-row x 32-column block, one row per lane.  Butterfly "transpose-reduce": in each
+// of 5 steps a lane keeps half of its columns and receives the partner's partial sums for them, so after 31 shuffles
+// lane l owns the sum over the 32 rows of column l.  Values are rounded to bf16 first (the statistics describe the
+// tensor as stored); rows beyond M contribute zero.  Deterministic: no atomics, one writer per workspace element.
+__device__ __forceinline__ float warp_column_sum(float* t, int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float keep = upper ? t[i + off] : t[i];
+      const float send = upper ? t[i] : t[i + off];
+      t[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return t[0];
+}
+
+__device__ __forceinline__ void column_stats_chunk(const GemmParams& p, int row, int row0, int col0, const float* v, int lane) {
+  float s[32], q[32];
+  const bool live = row < p.M;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const float r = p.out_fp32 ? v[i] : __bfloat162float(__float2bfloat16_rn(v[i]));
+    s[i] = live ? r : 0.f;
+    q[i] = s[i] * s[i];
+  }
+  const float cs = warp_column_sum(s, lane);
+  const float cq = warp_column_sum(q, lane);
+  const int col = col0 + lane;
+  if (col < p.N && row0 < p.M) {
+    const size_t g = (size_t)(row0 >> 5);
+    p.col_stats[(g) * p.N + col] = cs;
+    p.col_stats[((size_t)p.stat_groups + g) * p.N + col] = cq;
   }
 }
 
@@ -202,7 +242,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 
 // One warp drains its 32 accumulator rows x TILE_N columns.  `row0` = global row of lane 0, `slab` = running slab
 // counter of this warp (selects the staging buffer; persists across tiles).
-template <int TILE_N>
+template <int TILE_N, bool STATS>
 __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUtensorMap* map_d, uint8_t* stage, uint32_t taddr,
                                                   int row0, int n0, int lane, uint32_t& slab) {
 #pragma unroll 1
@@ -220,6 +260,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
       tmem_ld32(taddr + (uint32_t)(c + 32 * half), r);
       tmem_ld_wait();
       epilogue_math(p, n0 + c + 32 * half, r, v);
+      if constexpr (STATS) column_stats_chunk(p, row0 + lane, row0, n0 + c + 32 * half, v, lane);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         __nv_bfloat162 h[4];
@@ -251,7 +292,7 @@ struct SmemLayout {
   static constexpr int kTotal = kStages * kStageBytes + kBarrierBytes + 1024 /*alignment slack*/;
 };
 
-template <int BLOCK_N, bool A_MN, bool B_MN, bool TMA_ST>
+template <int BLOCK_N, bool A_MN, bool B_MN, bool TMA_ST, bool STATS>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_d, const GemmParams p) {
@@ -378,7 +419,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const int row = m0 + ew * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(accum * BLOCK_N);
       if constexpr (TMA_ST) {
-        epilogue_tile_tma<BLOCK_N>(p, &map_d, smem + kStages * L::kStageBytes + L::kBarrierBytes + ew * 2 * kStoreSlabBytes, taddr,
+        epilogue_tile_tma<BLOCK_N, STATS>(p, &map_d, smem + kStages * L::kStageBytes + L::kBarrierBytes + ew * 2 * kStoreSlabBytes, taddr,
                                    m0 + ew * 32, n0, lane, slab);
       } else {
 #pragma unroll 1
@@ -386,6 +427,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           uint32_t r[32];
           tmem_ld32(taddr + (uint32_t)c, r);
           tmem_ld_wait();
+          if constexpr (STATS) {
+            if (n0 + c < p.N) {                                   // warp-uniform
+              float v[32];
+              epilogue_math(p, n0 + c, r, v);
+              column_stats_chunk(p, row, m0 + ew * 32, n0 + c, v, lane);
+            }
+          }
           store_row_chunk(p, row, n0 + c, r);
         }
       }
@@ -451,7 +499,7 @@ struct SmemLayout2 {
   static constexpr int kTotal = kStages * kStageBytes + 1024 + 1024;
 };
 
-template <bool A_MN, bool B_MN, bool TMA_ST>
+template <bool A_MN, bool B_MN, bool TMA_ST, bool STATS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
 gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                       const __grid_constant__ CUtensorMap map_d, const GemmParams p) {
@@ -577,7 +625,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       const int row = m0 + ew * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(accum * BN);
       if constexpr (TMA_ST) {
-        epilogue_tile_tma<BN>(p, &map_d, smem + kStages * L::kStageBytes + 1024 + ew * 2 * kStoreSlabBytes, taddr, m0 + ew * 32, n0,
+        epilogue_tile_tma<BN, STATS>(p, &map_d, smem + kStages * L::kStageBytes + 1024 + ew * 2 * kStoreSlabBytes, taddr, m0 + ew * 32, n0,
                               lane, slab);
       } else {
 #pragma unroll 1
@@ -585,6 +633,13 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
           uint32_t r[32];
           tmem_ld32(taddr + (uint32_t)c, r);
           tmem_ld_wait();
+          if constexpr (STATS) {
+            if (n0 + c < p.N) {                                   // warp-uniform
+              float v[32];
+              epilogue_math(p, n0 + c, r, v);
+              column_stats_chunk(p, row, m0 + ew * 32, n0 + c, v, lane);
+            }
+          }
           store_row_chunk(p, row, n0 + c, r);
         }
       }
@@ -650,7 +705,7 @@ CUtensorMap make_map(const void* ptr, int rows, int cols, int box_rows, int box_
 }
 
 // TMA_ST: epilogue through shared memory + TMA store (bf16 output, N % 8 == 0); the D map's box is one warp slab.
-template <int BLOCK_N, bool A_MN, bool B_MN, bool TMA_ST>
+template <int BLOCK_N, bool A_MN, bool B_MN, bool TMA_ST, bool STATS = false>
 void launch_variant(const void* a, const void* b, const GemmParams& p, cudaStream_t stream) {
   using L = SmemLayout<BLOCK_N, A_MN, B_MN>;
   constexpr int kSmem = L::kTotal + (TMA_ST ? kStoreStageBytes : 0);
@@ -659,7 +714,7 @@ void launch_variant(const void* a, const void* b, const GemmParams& p, cudaStrea
   CUtensorMap map_a = A_MN ? make_map(a, p.K, p.M, BLOCK_K, 64) : make_map(a, p.M, p.K, BLOCK_M, BLOCK_K);
   CUtensorMap map_b = B_MN ? make_map(b, p.K, p.N, BLOCK_K, 64) : make_map(b, p.N, p.K, BLOCK_N, BLOCK_K);
   CUtensorMap map_d = TMA_ST ? make_map(p.d, p.M, p.N, 32, 64) : map_a;       // unused by the direct epilogue
-  auto kernel = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN, TMA_ST>;
+  auto kernel = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN, TMA_ST, STATS>;
   static bool configured = false;
   if (!configured) {
     B200_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
@@ -671,7 +726,7 @@ void launch_variant(const void* a, const void* b, const GemmParams& p, cudaStrea
   B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
 }
 
-template <bool A_MN, bool B_MN, bool TMA_ST>
+template <bool A_MN, bool B_MN, bool TMA_ST, bool STATS = false>
 void launch_variant_2cta(const void* a, const void* b, const GemmParams& p, cudaStream_t stream) {
   using L = SmemLayout2<A_MN, B_MN>;
   constexpr int kSmem = L::kTotal + (TMA_ST ? kStoreStageBytes : 0);
@@ -679,7 +734,7 @@ void launch_variant_2cta(const void* a, const void* b, const GemmParams& p, cuda
   CUtensorMap map_a = A_MN ? make_map(a, p.K, p.M, BLOCK_K, 64) : make_map(a, p.M, p.K, BLOCK_M, BLOCK_K);
   CUtensorMap map_b = B_MN ? make_map(b, p.K, p.N, BLOCK_K, 64) : make_map(b, p.N, p.K, L::BN / 2, BLOCK_K);
   CUtensorMap map_d = TMA_ST ? make_map(p.d, p.M, p.N, 32, 64) : map_a;
-  auto kernel = gemm_bf16_2cta_kernel<A_MN, B_MN, TMA_ST>;
+  auto kernel = gemm_bf16_2cta_kernel<A_MN, B_MN, TMA_ST, STATS>;
   static bool configured = false;
   if (!configured) {
     B200_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
@@ -710,7 +765,7 @@ bool gemm_shape_supported(int M, int N, int K, bool a_mn, bool b_mn) {
 }
 
 void launch_gemm_bf16(const void* a, const void* b, void* d, const void* bias, int M, int N, int K, bool a_mn, bool b_mn,
-                      int epilogue, DType out_dtype, bool accumulate, cudaStream_t stream) {
+                      int epilogue, DType out_dtype, bool accumulate, cudaStream_t stream, float* col_stats) {
   if (!gemm_shape_supported(M, N, K, a_mn, b_mn)) throw std::runtime_error("gemm_bf16: shape not TMA-compatible (row pitch % 16 B)");
   if (out_dtype != DType::BF16 && out_dtype != DType::F32) throw std::runtime_error("gemm_bf16: output must be bf16 or fp32");
   if (accumulate && out_dtype != DType::F32) throw std::runtime_error("gemm_bf16: accumulate needs fp32 output");
@@ -721,6 +776,8 @@ void launch_gemm_bf16(const void* a, const void* b, void* d, const void* bias, i
   p.accumulate = accumulate ? 1 : 0;
   p.d = d;
   p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
+  p.col_stats = col_stats;
+  p.stat_groups = (M + 31) / 32;
   if (g_gemm_mode == -1) {
     const char* e = getenv("B200DDP_GEMM_CTAS");
     g_gemm_mode = e ? atoi(e) : 0;
@@ -751,6 +808,20 @@ void launch_gemm_bf16(const void* a, const void* b, void* d, const void* bias, i
     if (N > 128 && cost_wide < best) { best = cost_wide; choice = 1; }
     if (M > 128 && N > 128 && cost_pair < best) { best = cost_pair; choice = 0; }
   }
+  if (col_stats != nullptr) {
+    // column statistics ride on the forward layout only (A [M,K], B [N,K]): that is where a normalisation follows
+    if (a_mn || b_mn) throw std::runtime_error("gemm_bf16: column statistics need K-major operands");
+    if (tma_st) {
+      if (choice == 0) launch_variant_2cta<false, false, true, true>(a, b, p, stream);
+      else if (choice == 1) launch_variant<256, false, false, true, true>(a, b, p, stream);
+      else launch_variant<128, false, false, true, true>(a, b, p, stream);
+    } else {
+      if (choice == 0) launch_variant_2cta<false, false, false, true>(a, b, p, stream);
+      else if (choice == 1) launch_variant<256, false, false, false, true>(a, b, p, stream);
+      else launch_variant<128, false, false, false, true>(a, b, p, stream);
+    }
+    return;
+  }
 #define B200_GEMM_DISPATCH(AMN, BMN)                                                   \
   if (a_mn == AMN && b_mn == BMN) {                                                    \
     if (tma_st) {                                                                      \
@@ -773,7 +844,7 @@ void launch_gemm_bf16(const void* a, const void* b, void* d, const void* bias, i
 
 void launch_gemm_nt_bf16(const void* a, const void* b, void* d, const void* bias, int M, int N, int K, int epilogue,
                          DType out_dtype, cudaStream_t stream) {
-  launch_gemm_bf16(a, b, d, bias, M, N, K, false, false, epilogue, out_dtype, false, stream);
+  launch_gemm_bf16(a, b, d, bias, M, N, K, false, false, epilogue, out_dtype, false, stream, nullptr);
 }
 
 }  // namespace b200

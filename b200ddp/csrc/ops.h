@@ -74,6 +74,12 @@ void launch_bn_forward(const void* x, const void* residual, void* y, unsigned ch
                        float* running_mean, float* running_var, long long* num_batches, float* save_mean, float* save_rstd,
                        float* scale, float* shift, float* partial, unsigned int* counters, float eps, float momentum, bool relu,
                        cudaStream_t s);
+// Same as launch_bn_forward, but the statistics come from `partial` = [2][groups][C] partial column sums / sums of squares
+// (written by the GEMM epilogue that produced x): finish kernel + apply kernel, x is read once instead of twice.
+void launch_bn_forward_from_partials(const void* x, const void* residual, void* y, unsigned char* relu_mask, DType dt, int R, int C,
+                                     const float* gamma, const float* beta, float* running_mean, float* running_var,
+                                     long long* num_batches, float* save_mean, float* save_rstd, float* scale, float* shift,
+                                     const float* partial, int groups, float eps, float momentum, bool relu, cudaStream_t s);
 void launch_bn_backward(const void* dy, const void* x, const void* relu_mask, void* dx, void* dres, DType dt, int R, int C, const float* gamma,
                         const float* save_mean, const float* save_rstd, float* dgamma, float* dbeta, float* coef, float* partial,
                         unsigned int* counters, bool relu, cudaStream_t s);

@@ -27,9 +27,18 @@ class Bottleneck(nn.Module):
         self.conv3 = PointwiseConv2d(planes, planes * self.expansion)
         self.bn3 = FusedBatchNormAct2d(planes * self.expansion, relu=True)
         self.downsample = downsample
+        # opt-in (B200DDP_CONV1X1_TC=1 and B200DDP_CONV_BN_FUSE=1): the 1x1 convolutions' GEMM epilogue hands BatchNorm its
+        # statistics, so bn1 / bn3 read their input once instead of twice
+        self.fuse_stats = os.environ.get("B200DDP_CONV_BN_FUSE", "0") == "1" and self.conv1.use_tc
 
     def forward(self, x):
         identity = x if self.downsample is None else self.downsample(x)
+        if self.fuse_stats:
+            y, part = self.conv1.forward_with_stats(x)
+            out = self.bn1(y, partials=part)
+            out = self.bn2(self.conv2(out))
+            y, part = self.conv3.forward_with_stats(out)
+            return self.bn3(y, residual=identity, partials=part)
         out = self.bn1(self.conv1(x))
         out = self.bn2(self.conv2(out))
         return self.bn3(self.conv3(out), residual=identity)

@@ -16,12 +16,17 @@ from .. import _ext
 
 class _FusedBN(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, residual, weight, bias, module, relu):
+    def forward(ctx, x, residual, weight, bias, module, relu, partials=None):
         C = _ext.get()
         ws = module._workspace(x)
-        y, stats, mask = C.bn_forward(x, residual, weight, bias, module.running_mean, module.running_var,
-                                      module.num_batches_tracked, module.eps,
-                                      module.momentum if module.momentum is not None else 0.1, relu, ws[0], ws[1])
+        momentum = module.momentum if module.momentum is not None else 0.1
+        if partials is not None:
+            # statistics already reduced per 32-row group by the producing GEMM: finish + apply, x is read once
+            y, stats, mask = C.bn_forward_partials(x, residual, weight, bias, module.running_mean, module.running_var,
+                                                   module.num_batches_tracked, module.eps, momentum, relu, partials)
+        else:
+            y, stats, mask = C.bn_forward(x, residual, weight, bias, module.running_mean, module.running_var,
+                                          module.num_batches_tracked, module.eps, momentum, relu, ws[0], ws[1])
         ctx.save_for_backward(x, mask if relu else None, weight, stats)    # 1 bit / element instead of keeping y for the mask
         ctx.relu = relu
         ctx.has_residual = residual is not None
@@ -37,7 +42,7 @@ class _FusedBN(torch.autograd.Function):
         dx, dres, dparams = C.bn_backward(dy, x, y, weight, stats, ctx.relu, need_dres, ws[2], ws[3])
         if ctx.has_residual and not ctx.relu:
             dres = dy                                  # plain add: the shortcut receives dy unchanged
-        return dx, (dres if ctx.has_residual else None), dparams[0], dparams[1], None, None
+        return dx, (dres if ctx.has_residual else None), dparams[0], dparams[1], None, None, None
 
 
 class FusedBatchNormAct2d(nn.BatchNorm2d):
@@ -64,11 +69,14 @@ class FusedBatchNormAct2d(nn.BatchNorm2d):
                 and x.dtype in (torch.bfloat16, torch.float32) and self.weight is not None and self.weight.dtype == torch.float32
                 and x.is_contiguous(memory_format=torch.channels_last))
 
-    def forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None,
+                partials: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``partials``: optional [2, groups, C] partial statistics of ``x`` from the kernel that produced it
+        (``functional.conv1x1_stats``); ignored on the stock fallback path, which recomputes them."""
         if self._fusable(x) and (residual is None or (residual.dtype == x.dtype and residual.shape == x.shape)):
             if residual is not None and not residual.is_contiguous(memory_format=torch.channels_last):
                 residual = residual.contiguous(memory_format=torch.channels_last)
-            return _FusedBN.apply(x, residual, self.weight, self.bias, self, self.relu)
+            return _FusedBN.apply(x, residual, self.weight, self.bias, self, self.relu, partials)
         y = super().forward(x)
         if residual is not None:
             y = y + residual

@@ -146,6 +146,41 @@ def conv1x1(x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
     return y2.view(n, h, w, co).permute(0, 3, 1, 2)             # channels_last-strided [N, C_out, H, W]
 
 
+class _Conv1x1Stats(torch.autograd.Function):
+    """``_LinearTC`` without bias whose forward GEMM also emits the partial column statistics of its output
+    ([2, ceil(M/32), N] fp32: per-32-row sums and sums of squares) for the BatchNorm that follows."""
+
+    @staticmethod
+    def forward(ctx, x2, w2):
+        y2, partials = _C().gemm_stats(x2, w2)
+        ctx.save_for_backward(x2, w2)
+        ctx.mark_non_differentiable(partials)
+        return y2, partials
+
+    @staticmethod
+    def backward(ctx, dy, _dpartials):
+        C = _C()
+        x2, w2 = ctx.saved_tensors
+        dy2 = dy if dy.is_contiguous() else dy.contiguous()
+        dx = C.gemm(dy2, w2, None, False, True, EPI_NONE, False, None) if ctx.needs_input_grad[0] else None
+        dw = C.gemm(dy2, x2, None, True, True, EPI_NONE, False, None) if ctx.needs_input_grad[1] else None
+        return dx, dw
+
+
+def conv1x1_stats(x: torch.Tensor, weight: torch.Tensor):
+    """``conv1x1`` that also returns the BatchNorm partial statistics computed in the GEMM epilogue (or ``None`` when
+    the tensor-core path does not apply and the caller should let BatchNorm compute its own)."""
+    n, c, h, w = x.shape
+    co = weight.shape[0]
+    ok = (x.is_cuda and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and weight.shape[2:] == (1, 1)
+          and x.is_contiguous(memory_format=torch.channels_last) and _tc_ok(n * h * w, co, c))
+    if not ok:
+        return F.conv2d(x, weight), None
+    x2 = x.permute(0, 2, 3, 1).reshape(n * h * w, c)
+    y2, partials = _Conv1x1Stats.apply(x2, weight.reshape(co, c))
+    return y2.view(n, h, w, co).permute(0, 3, 1, 2), partials
+
+
 # ------------------------------------------------------------------------------------------------
 # Losses: forward computes loss AND input gradient in one launch
 # ------------------------------------------------------------------------------------------------

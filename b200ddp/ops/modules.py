@@ -52,6 +52,12 @@ class PointwiseConv2d(nn.Conv2d):
             return Fn.conv1x1(x, self.weight)
         return super().forward(x)
 
+    def forward_with_stats(self, x: torch.Tensor):
+        """(y, partial BatchNorm statistics from the GEMM epilogue) - statistics are ``None`` off the tensor-core path."""
+        if self.use_tc and x.is_cuda:
+            return Fn.conv1x1_stats(x, self.weight)
+        return super().forward(x), None
+
 
 class LayerNorm(nn.Module):
     def __init__(self, hidden: int, eps: float = 1e-5, device=None, dtype=None):

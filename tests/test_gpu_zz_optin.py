@@ -84,3 +84,61 @@ def test_data_parallel_matches_single_device():
     for p, q in zip(single.parameters(), multi.parameters()):
         assert torch.allclose(p.grad, q.grad, atol=1e-5)
     assert set(dp.state_dict()) == set(single.state_dict())        # no "module." prefix in checkpoints
+
+
+@unvalidated
+@pytest.mark.parametrize("mode,tma", [(1, 0), (2, 0), (1, 1), (2, 1)])
+@pytest.mark.parametrize("M,N,K", [(1000, 264, 72), (25088, 256, 64), (6272, 1024, 256), (304, 64, 512)])
+def test_gemm_epilogue_column_statistics(mode, tma, M, N, K):
+    """Per-32-row partial column sums / sums of squares written by the GEMM epilogue == the same sums of its stored output."""
+    from b200ddp import _ext
+    C = _ext.get()
+    torch.manual_seed(3)
+    a = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+    b = torch.randn(N, K, device="cuda", dtype=torch.bfloat16) * 0.2
+    try:
+        C.set_gemm_cta_mode(mode)
+        C.set_gemm_tma_store(tma)
+        d, st = C.gemm_stats(a, b)
+        d0 = C.gemm(a, b, None, False, False, 0, False, None)
+    finally:
+        C.set_gemm_tma_store(0)
+        C.set_gemm_cta_mode(0)
+    assert torch.equal(d, d0)
+    G = (M + 31) // 32
+    assert st.shape == (2, G, N)
+    pad = torch.zeros(G * 32, N, device="cuda")
+    pad[:M] = d.float()
+    grp = pad.view(G, 32, N)
+    assert torch.allclose(st[0], grp.sum(1), atol=1e-3, rtol=1e-4)
+    assert torch.allclose(st[1], grp.square().sum(1), atol=1e-2, rtol=1e-4)
+
+
+@unvalidated
+def test_bottleneck_with_stats_from_the_gemm_epilogue(monkeypatch):
+    from b200ddp.models.resnet import Bottleneck
+    from b200ddp.utils import to_mixed_bf16
+    monkeypatch.setenv("B200DDP_CONV1X1_TC", "1")
+    torch.manual_seed(0)
+    monkeypatch.setenv("B200DDP_CONV_BN_FUSE", "0")
+    ref = to_mixed_bf16(Bottleneck(256, 64).cuda()).to(memory_format=torch.channels_last)
+    monkeypatch.setenv("B200DDP_CONV_BN_FUSE", "1")
+    fused = to_mixed_bf16(Bottleneck(256, 64).cuda()).to(memory_format=torch.channels_last)
+    assert fused.fuse_stats and not ref.fuse_stats
+    fused.load_state_dict(ref.state_dict())
+    x = torch.randn(16, 256, 28, 28, device="cuda", dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    ya, yb = ref(xa), fused(xb)
+    g = torch.randn_like(ya)
+    ya.backward(g)
+    yb.backward(g)
+
+    def rel(u, v):
+        return float((u.float() - v.float()).norm() / (v.float().norm() + 1e-12))
+    assert rel(yb, ya) < 2e-2
+    assert rel(xb.grad, xa.grad) < 3e-2
+    for (k, p), (_, q) in zip(ref.named_parameters(), fused.named_parameters()):
+        if p.grad.float().norm() > 1e-3:
+            assert rel(q.grad, p.grad) < 5e-2, k
+    for (k, u), (_, v) in zip(ref.named_buffers(), fused.named_buffers()):
+        assert torch.allclose(u.float(), v.float(), atol=1e-2, rtol=1e-2), k

@@ -25,6 +25,7 @@ run base_again A=0
 run stem_pad8 B200DDP_STEM_PAD=8
 run conv1x1_tc B200DDP_CONV1X1_TC=1
 run conv1x1_tc_tmastore B200DDP_CONV1X1_TC=1 B200DDP_GEMM_TMA_STORE=1
+run conv1x1_tc_tmastore_bnfuse B200DDP_CONV1X1_TC=1 B200DDP_GEMM_TMA_STORE=1 B200DDP_CONV_BN_FUSE=1
 run conv1x1_tc_group8 B200DDP_CONV1X1_TC=1 B200DDP_GEMM_GROUP_M=8
 run stem_pad8_conv1x1 B200DDP_STEM_PAD=8 B200DDP_CONV1X1_TC=1
 run bn_fused B200DDP_BN_FUSED=1
