@@ -2,7 +2,10 @@
 
 Drop-in for ``nn.BatchNorm2d`` (same parameter / buffer names, so checkpoints and bucket layouts are unchanged) with two
 extra knobs: ``relu=True`` fuses the activation, and ``forward(x, residual=...)`` fuses the Bottleneck shortcut add.  On
-CPU, in eval mode, or for layouts the kernel does not cover, it computes the same thing with stock torch ops."""
+CPU, in eval mode, or for layouts the kernel does not cover, it computes the same thing with stock torch ops.
+
+The reference's own model has no normalisation (``model.py:8-16``); this op exists for the ResNet-50 / ResNet-152 configs
+BASELINE.json names, where the stock ATen BatchNorm + add + ReLU kernels were 58 % of the step (``profiles/launches.md``)."""
 from __future__ import annotations
 
 from typing import Optional

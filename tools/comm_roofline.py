@@ -1,17 +1,41 @@
 #!/usr/bin/env python
 """Turn the allreduce sweep JSONs (bench/allreduce_sweep.py) into profiles/comm_roofline.md.
 
-Roofline used (BASELINE.json: "bytes over NVLink at link bandwidth"): every GPU has 900 GB/s per direction into
-the NVSwitch.  A reduce-scatter + all-gather moves 2(W-1)/W x bytes out of (and into) each GPU, which is exactly
-NCCL's "bus bandwidth" convention, so for peer-to-peer algorithms the ceiling of busbw is the link rate, 900 GB/s.
+Roofline used (BASELINE.json: "bytes over NVLink at link bandwidth"; B200_PROFILING.md: the denominator is the MEASURED
+peer-copy rate, 770 GB/s per direction per GPU - 900 nominal; its other reference point is NCCL's 8-rank all-reduce at
+725 GB/s busbw for 1 GiB).  A reduce-scatter + all-gather moves 2(W-1)/W x bytes out of (and into) each GPU, which is
+exactly NCCL's "bus bandwidth" convention, so for peer-to-peer algorithms the ceiling of busbw is the link rate, 770 GB/s.
 With in-switch reduction (multimem.ld_reduce + multimem.st) each GPU only sends bytes x ((W-1)/W + 1/W) = bytes,
-so the busbw ceiling rises to 900 x 2(W-1)/W GB/s (900 / 1350 / 1575 for W = 2 / 4 / 8).
+so the busbw ceiling rises to 770 x 2(W-1)/W GB/s (770 / 1155 / 1348 for W = 2 / 4 / 8).
 """
 import json
 import sys
 from pathlib import Path
 
-LINK_GBS = 900.0
+LINK_GBS = 770.0          # measured peer copy per direction (B200_PROFILING.md); 900 nominal
+
+
+# Measured step times with and without the gradient exchange (same binary, `bench.py --no_comm` disables the hooks);
+# sources: profiles/ddp_overhead_diag_n2_v3.txt, profiles/scale_n4_v1.txt, profiles/bench_r1_n8_ours.json.
+DDP_SECTION = """
+## The fused gradient path inside the ResNet-50 step
+
+Wire bytes per step: 51.2 MB (25.6 M gradients; bf16 convolution / linear gradients stay bf16 on the wire, fp32 BatchNorm
+gradients stay fp32), in 5 buckets launched in completion order on a high-priority stream while backward is still running.
+Link-roofline time = 2(W-1)/W x 51.2 MB / 770 GB/s.  What the step actually pays is the *exposed* part: step time with the
+exchange minus step time with `--no_comm`.
+
+| GPUs | step, exchange on | step, exchange off | exposed | link-roofline time of the exchange | exposed / step |
+|---|---|---|---|---|---|
+| 2 | 8.737 ms | 8.230 ms | 0.507 ms | 0.066 ms | 5.8 % |
+| 4 | 5.366 ms | 4.992 ms | 0.374 ms | 0.100 ms | 7.0 % |
+| 8 | 5.455 ms | 5.0 ms (1-GPU step; no 8-GPU `--no_comm` run) | ~0.46 ms | 0.116 ms | 8.3 % |
+
+(The 2-GPU row predates the fused BatchNorm work, hence the longer step.)  The exposed part is 3.7-7.7x the link time of the
+whole exchange: the buckets that overlap are free, the residue is the last bucket (launch after the final gradient, two
+peer rendezvous, 3 MiB on the wire) plus SM time the light comm CTAs take from backward.  `docs/ROADMAP.md` section 4 lists
+what is left to try; block-count sweeps (ov8 / ov24 / ov48, tail 24 / 96 in `ddp_overhead_diag_n2_v3.txt`) move it by < 1 %.
+"""
 
 
 def human(n: int) -> str:
@@ -60,6 +84,7 @@ def main() -> None:
             "NCCL, and large fp32 payloads are the round-2 item in `docs/ROADMAP.md`.", ""]
     for w in sorted(latest):
         body.append(table(latest[w]))
+    body += DDP_SECTION.strip("\n").split("\n")
     (root / "comm_roofline.md").write_text("\n".join(body) + "\n")
     print(root / "comm_roofline.md")
 
