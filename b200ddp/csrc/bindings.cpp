@@ -1,4 +1,5 @@
-// Python bindings.  The only translation unit that sees torch headers.
+// Python bindings.  The only translation unit that sees torch headers.  Which reference call site each op stands in for is
+// documented on the Python side (b200ddp/ops/functional.py, parallel/peer.py, optim/sgd.py) and in docs/INVENTORY.md.
 #include <torch/extension.h>
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>

@@ -1,5 +1,6 @@
 // Device-side building blocks for the peer-memory collectives: system-scope signal primitives,
 // the block-wise cross-GPU barrier, multimem (NVLS) accessors and the bucket tensor table.
+// (the transport the reference gets from ProcessGroupNCCL, `init_process_group("nccl")` at ddp.py:103.)
 #pragma once
 #include "common.h"
 #include "peer_mem.h"
