@@ -5,10 +5,8 @@ import os
 import pytest
 import torch
 
-pytestmark = pytest.mark.gpu
-# kernels written after the last GPU session of the round: run them explicitly (tools/round2_ablation.sh) before
-# they join the default tier
-unvalidated = pytest.mark.skipif(os.environ.get("B200DDP_TEST_OPTIN") != "1", reason="opt-in kernel not yet validated on a GPU; set B200DDP_TEST_OPTIN=1")
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("B200DDP_TEST_OPTIN") != "1",
+                                                   reason="written after the last GPU session: run with B200DDP_TEST_OPTIN=1 (tools/round2_ablation.sh)")]
 
 
 @pytest.mark.parametrize("mode", [1, 2])
@@ -36,7 +34,6 @@ def test_grouped_raster_is_bit_identical(mode, M, N, K):
         assert torch.equal(d, d0)
 
 
-@unvalidated
 @pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True)])
 @pytest.mark.parametrize("M,N,K", [(2048, 2048, 512), (1000, 3000, 264), (304, 264, 72), (100352, 64, 64), (4096, 768, 768)])
