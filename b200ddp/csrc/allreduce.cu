@@ -360,6 +360,9 @@ void launch_symmetric_allreduce(const CommCtx& ctx, size_t buf_off, size_t numel
   if (algo != kAlgoTwoShot && algo != kAlgoNvls) throw std::runtime_error("symmetric allreduce: two_shot or nvls");
   const size_t ve = dtype == DType::BF16 ? 8 : 4;
   if (numel % ve != 0 || buf_off % 16 != 0) throw std::runtime_error("symmetric allreduce: buffer must be 16-byte granular");
+  if (numel > 0xFFFFFFF0ull) throw std::runtime_error("symmetric allreduce: more than 2^32 elements in one call (element offsets are 32-bit)");
+  if (blocks < 1 || blocks > kMaxCommBlocks) throw std::runtime_error("symmetric allreduce: bad block count");
+  if (algo == kAlgoNvls && ctx.mc_base == nullptr) throw std::runtime_error("symmetric allreduce: NVLS requested without multicast");
   BucketTable tab;
   tab.count = 0;
   tab.data_elems = (uint32_t)numel;
