@@ -6,6 +6,7 @@
 
 #include "comm.h"
 #include "comm_kernels.cuh"
+#include "conv.h"
 #include "gemm.h"
 #include "ops.h"
 #include "peer_mem.h"
@@ -471,6 +472,25 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     std::vector<std::pair<int, int>> out((size_t)num_m * num_n);
     for (int t = 0; t < num_m * num_n; ++t) gemm_tile_coords(t, num_m, num_n, group_m, &out[t].first, &out[t].second);
     return out;
+  });
+
+  // ---- experimental: 3x3 convolution forward as nine shifted tcgen05 GEMMs (conv3x3_tcgen05.cu) -----
+  m.def("conv3x3_fwd", [](at::Tensor x, at::Tensor w) {
+    check_cuda(x, "x"); check_cuda(w, "w");
+    TORCH_CHECK(x.scalar_type() == at::kBFloat16 && w.scalar_type() == at::kBFloat16, "conv3x3_fwd: bf16 tensors");
+    TORCH_CHECK(x.dim() == 4 && x.is_contiguous(at::MemoryFormat::ChannelsLast), "conv3x3_fwd: x must be 4-D channels_last");
+    TORCH_CHECK(w.dim() == 4 && w.size(2) == 3 && w.size(3) == 3 && w.size(1) == x.size(1) && w.is_contiguous(at::MemoryFormat::ChannelsLast),
+                "conv3x3_fwd: filter must be [K, C, 3, 3] channels_last (stored [K][3][3][C])");
+    c10::cuda::CUDAGuard guard(x.device());
+    const int N = (int)x.size(0), C = (int)x.size(1), H = (int)x.size(2), W = (int)x.size(3), K = (int)w.size(0);
+    at::Tensor y = at::empty({N, K, H, W}, x.options().memory_format(at::MemoryFormat::ChannelsLast));
+    launch_conv3x3_fprop(x.data_ptr(), w.data_ptr(), y.data_ptr(), N, H, W, C, K, cur_stream());
+    return y;
+  });
+  m.def("conv3x3_patch", [](int N, int H, int W) {
+    int bh = 0, bi = 0;
+    const bool ok = conv3x3_patch(N, H, W, &bh, &bi);
+    return std::make_tuple(ok, bh, bi);
   });
 
   // ---- fused BatchNorm ---------------------------------------------------------------------------

@@ -139,3 +139,19 @@ def test_bottleneck_with_stats_from_the_gemm_epilogue(monkeypatch):
             assert rel(q.grad, p.grad) < 5e-2, k
     for (k, u), (_, v) in zip(ref.named_buffers(), fused.named_buffers()):
         assert torch.allclose(u.float(), v.float(), atol=1e-2, rtol=1e-2), k
+
+
+@pytest.mark.parametrize("N,C,H,W,K", [(32, 64, 56, 56, 64), (32, 128, 28, 28, 128), (32, 256, 14, 14, 256), (32, 512, 7, 7, 512),
+                                       (3, 64, 7, 7, 24), (4, 64, 12, 20, 72)])
+def test_conv3x3_nine_shifted_gemms_matches_cudnn(N, C, H, W, K):
+    """Experimental tcgen05 3x3 convolution forward (csrc/conv3x3_tcgen05.cu) vs F.conv2d."""
+    from b200ddp import _ext
+    Cx = _ext.get()
+    torch.manual_seed(0)
+    x = torch.randn(N, C, H, W, device="cuda", dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(K, C, 3, 3, device="cuda") * 0.05).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    y = Cx.conv3x3_fwd(x, w)
+    ref = torch.nn.functional.conv2d(x.float(), w.float(), padding=1)
+    assert y.shape == ref.shape and y.is_contiguous(memory_format=torch.channels_last)
+    err = float((y.float() - ref).norm() / ref.norm())
+    assert err < 1e-2, err
