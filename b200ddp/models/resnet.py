@@ -11,7 +11,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from ..ops import FusedBatchNormAct2d, Linear, MaxPool3x3s2, PointwiseConv2d
+from ..ops import Conv3x3, FusedBatchNormAct2d, Linear, MaxPool3x3s2, PointwiseConv2d
 
 
 class Bottleneck(nn.Module):
@@ -22,7 +22,7 @@ class Bottleneck(nn.Module):
         # BatchNorm + ReLU (and, for bn3, the shortcut add) are single fused kernels on channels_last CUDA tensors
         self.conv1 = PointwiseConv2d(inplanes, planes)
         self.bn1 = FusedBatchNormAct2d(planes, relu=True)
-        self.conv2 = nn.Conv2d(planes, planes, 3, stride=stride, padding=1, bias=False)
+        self.conv2 = Conv3x3(planes, planes, stride=stride)
         self.bn2 = FusedBatchNormAct2d(planes, relu=True)
         self.conv3 = PointwiseConv2d(planes, planes * self.expansion)
         self.bn3 = FusedBatchNormAct2d(planes * self.expansion, relu=True)

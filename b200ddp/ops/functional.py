@@ -182,6 +182,48 @@ def conv1x1_stats(x: torch.Tensor, weight: torch.Tensor):
 
 
 # ------------------------------------------------------------------------------------------------
+# 3x3 convolution (experimental, opt-in): forward and dgrad on the nine-shifted-GEMM kernel
+# ------------------------------------------------------------------------------------------------
+def _conv3x3_fprop(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """stride-1 / pad-1 3x3 convolution: ``csrc/conv3x3_tcgen05.cu`` for channels_last bf16 CUDA tensors it covers,
+    the stock op otherwise (CPU tests exercise the surrounding autograd logic through this fallback)."""
+    if (x.is_cuda and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and x.shape[1] % 64 == 0 and w.shape[0] % 8 == 0
+            and x.shape[3] <= 128):
+        xc = x if x.is_contiguous(memory_format=torch.channels_last) else x.contiguous(memory_format=torch.channels_last)
+        wc = w if w.is_contiguous(memory_format=torch.channels_last) else w.contiguous(memory_format=torch.channels_last)
+        return _C().conv3x3_fwd(xc, wc)
+    return F.conv2d(x, w, padding=1)
+
+
+class _Conv3x3TC(torch.autograd.Function):
+    """fprop and dgrad are the same kernel: dx = conv3x3(dy, W') with W'[ci, co, r, s] = W[co, ci, 2-r, 2-s] (a
+    few-hundred-KB permutation per layer); wgrad stays on the library (``aten::convolution_backward``) until the split-K
+    tcgen05 version exists."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        ctx.save_for_backward(x, w)
+        return _conv3x3_fprop(x, w)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            w_t = w.flip(2, 3).transpose(0, 1)
+            dx = _conv3x3_fprop(dy, w_t.contiguous(memory_format=torch.channels_last) if w.is_cuda else w_t)
+        if ctx.needs_input_grad[1]:
+            dw = torch.ops.aten.convolution_backward(dy, x, w, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1,
+                                                     [False, True, False])[1]
+        return dx, dw
+
+
+def conv3x3(x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    """3x3, stride 1, zero padding 1, no bias."""
+    return _Conv3x3TC.apply(x, weight)
+
+
+# ------------------------------------------------------------------------------------------------
 # Losses: forward computes loss AND input gradient in one launch
 # ------------------------------------------------------------------------------------------------
 class _MSEFused(torch.autograd.Function):

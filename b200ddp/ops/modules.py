@@ -60,6 +60,23 @@ class PointwiseConv2d(nn.Conv2d):
         return super().forward(x), None
 
 
+class Conv3x3(nn.Conv2d):
+    """3x3 / pad 1 bias-free ``nn.Conv2d`` (same parameter name, shape, init).  Default: cuDNN.  Opt-in
+    (``B200DDP_CONV3X3_TC=1`` at construction, or ``use_tc=True``): stride-1 instances run forward and dgrad on the
+    experimental nine-shifted-GEMM tcgen05 kernel (``functional.conv3x3``)."""
+
+    def __init__(self, in_channels: int, out_channels: int, stride: int = 1, use_tc: Optional[bool] = None, **kw):
+        super().__init__(in_channels, out_channels, 3, stride=stride, padding=1, bias=False, **kw)
+        if use_tc is None:
+            use_tc = os.environ.get("B200DDP_CONV3X3_TC", "0") == "1"
+        self.use_tc = bool(use_tc) and self.stride == (1, 1)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self.use_tc:
+            return Fn.conv3x3(x, self.weight)
+        return super().forward(x)
+
+
 class LayerNorm(nn.Module):
     def __init__(self, hidden: int, eps: float = 1e-5, device=None, dtype=None):
         super().__init__()

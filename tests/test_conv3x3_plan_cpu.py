@@ -64,3 +64,22 @@ def test_nine_shifted_gemms_equal_the_convolution(N, C, H, W, K):
     w = torch.randn(K, C, 3, 3) * 0.1
     ref = F.conv2d(x, w, padding=1)
     assert torch.allclose(emulate(x, w), ref, atol=1e-3, rtol=1e-4)
+
+
+def test_conv3x3_function_gradients_match_autograd():
+    """dgrad as a forward convolution with the mirrored, transposed filter; wgrad from aten::convolution_backward."""
+    from b200ddp.ops import Conv3x3, conv3x3
+    torch.manual_seed(0)
+    x = torch.randn(2, 8, 9, 7, requires_grad=True)
+    w = (torch.randn(6, 8, 3, 3) * 0.2).requires_grad_(True)
+    x2, w2 = x.detach().clone().requires_grad_(True), w.detach().clone().requires_grad_(True)
+    g = torch.randn(2, 6, 9, 7)
+    conv3x3(x, w).backward(g)
+    F.conv2d(x2, w2, padding=1).backward(g)
+    assert torch.allclose(x.grad, x2.grad, atol=1e-4)
+    assert torch.allclose(w.grad, w2.grad, atol=1e-4)
+    m = Conv3x3(8, 6, use_tc=True)
+    ref = torch.nn.Conv2d(8, 6, 3, padding=1, bias=False)
+    ref.load_state_dict(m.state_dict())
+    assert torch.allclose(m(x2.detach()), ref(x2.detach()), atol=1e-5)
+    assert not Conv3x3(8, 6, stride=2, use_tc=True).use_tc        # strided instances stay on the library

@@ -155,3 +155,21 @@ def test_conv3x3_nine_shifted_gemms_matches_cudnn(N, C, H, W, K):
     assert y.shape == ref.shape and y.is_contiguous(memory_format=torch.channels_last)
     err = float((y.float() - ref).norm() / ref.norm())
     assert err < 1e-2, err
+
+
+def test_conv3x3_module_forward_and_dgrad_on_the_draft_kernel():
+    from b200ddp.ops import Conv3x3
+    torch.manual_seed(0)
+    ref = Conv3x3(128, 128, use_tc=False).cuda().bfloat16().to(memory_format=torch.channels_last)
+    tc = Conv3x3(128, 128, use_tc=True).cuda().bfloat16().to(memory_format=torch.channels_last)
+    tc.load_state_dict(ref.state_dict())
+    x = torch.randn(8, 128, 28, 28, device="cuda", dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    ya, yb = ref(xa), tc(xb)
+    g = torch.randn_like(ya)
+    ya.backward(g)
+    yb.backward(g)
+
+    def rel(u, v):
+        return float((u.float() - v.float()).norm() / (v.float().norm() + 1e-12))
+    assert rel(yb, ya) < 1e-2 and rel(xb.grad, xa.grad) < 1e-2 and rel(tc.weight.grad, ref.weight.grad) < 1e-2
