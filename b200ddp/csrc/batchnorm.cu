@@ -75,6 +75,11 @@ __device__ __forceinline__ void bn_apply_rows(const T* __restrict__ x, const T* 
                                               unsigned char* __restrict__ mask, const float* __restrict__ scale,
                                               const float* __restrict__ shift, int C, int cv, int r0, int r1, int tyi, int ty, int relu);
 
+// Programmatic dependent launch (opt-in, B200DDP_PDL=1): the producer lets the dependent grid start scheduling once its
+// main loop is done; the dependent blocks at griddepcontrol.wait until the producer grid has completed and flushed.
+__device__ __forceinline__ void bn_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void bn_wait_producer() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // release/acquire on the per-tile generation word used by the fused (single-launch) variants
 __device__ __forceinline__ void bn_st_release(unsigned int* p, unsigned int v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ unsigned int bn_ld_acquire(const unsigned int* p) {
@@ -97,7 +102,7 @@ __device__ __forceinline__ void bn_wait_generation(const unsigned int* p, unsign
 // FUSED = true: statistics AND normalisation in ONE launch.  All blocks of a channel tile rendezvous on a
 // generation word after the tile's last block has finished the statistics (the grid is sized to be co-resident:
 // <= 2 blocks per SM), then every block normalises exactly the rows it has just read (L2-hot).
-template <typename T, bool FUSED>
+template <typename T, bool FUSED, bool PDL = false>
 __global__ void __launch_bounds__(kBnThreads, 2) bn_stats_kernel(const T* __restrict__ x, int R, int C, int cvb, int ty,
                                                              float* __restrict__ partial /*[2][S][C]*/, unsigned int* __restrict__ counters,
                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -138,6 +143,7 @@ __global__ void __launch_bounds__(kBnThreads, 2) bn_stats_kernel(const T* __rest
       for (int i = 0; i < kVec; ++i) { acc[0][i] += f[i]; acc[1][i] = fmaf(f[i], f[i], acc[1][i]); }
     }
   }
+  if constexpr (PDL) bn_launch_dependents();       // the apply kernel may start scheduling; it still waits for this whole grid
   reduce_rows<2>(acc, smem, tx, tyi, cvb, ty);
   const int width = cvb * kVec;
   const int c0 = blockIdx.x * width;
@@ -265,6 +271,21 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const T* __restric
   bn_apply_rows<T>(x, residual, y, mask, scale, shift, C, cv, r0, r1, tyi, ty, relu);
 }
 
+// same body, launched as a programmatic dependent of bn_stats_kernel<.., PDL = true>
+template <typename T>
+__global__ void __launch_bounds__(kBnThreads) bn_apply_pdl_kernel(const T* __restrict__ x, const T* __restrict__ residual, T* __restrict__ y,
+                                                                 unsigned char* __restrict__ mask, const float* __restrict__ scale,
+                                                                 const float* __restrict__ shift, int R, int C, int cvb, int ty, int relu) {
+  const int tx = threadIdx.x % cvb, tyi = threadIdx.x / cvb;
+  const int cv = blockIdx.x * cvb + tx;
+  const int S = gridDim.y;
+  const int rows_per = (R + S - 1) / S;
+  const int r0 = blockIdx.y * rows_per, r1 = min(R, r0 + rows_per);
+  bn_wait_producer();                               // scale / shift are written by the producer's last block
+  if (cv * kVec >= C) return;
+  bn_apply_rows<T>(x, residual, y, mask, scale, shift, C, cv, r0, r1, tyi, ty, relu);
+}
+
 template <typename T>
 __device__ __forceinline__ void bn_bwd_apply_rows(const T* __restrict__ dy, const T* __restrict__ x, const unsigned char* __restrict__ y,
                                                   T* __restrict__ dx, T* __restrict__ dres, const float* __restrict__ save_mean,
@@ -272,7 +293,7 @@ __device__ __forceinline__ void bn_bwd_apply_rows(const T* __restrict__ dy, cons
                                                   const float* __restrict__ coef, int C, int cv, int r0, int r1, int tyi, int ty, int relu);
 
 // ------------------------------------------------------------------------------------------------------
-template <typename T, bool FUSED>
+template <typename T, bool FUSED, bool PDL = false>
 __global__ void __launch_bounds__(kBnThreads, 2) bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const unsigned char* __restrict__ y,
                                                                      int R, int C, int cvb, int ty, int relu, const float* __restrict__ save_mean,
                                                                      const float* __restrict__ save_rstd, float* __restrict__ partial,
@@ -331,6 +352,7 @@ __global__ void __launch_bounds__(kBnThreads, 2) bn_bwd_reduce_kernel(const T* _
       }
     }
   }
+  if constexpr (PDL) bn_launch_dependents();       // the apply kernel may start scheduling; it still waits for this whole grid
   reduce_rows<2>(acc, smem, tx, tyi, cvb, ty);
   const int width = cvb * kVec;
   const int c0 = blockIdx.x * width;
@@ -464,6 +486,43 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const T* __res
   bn_bwd_apply_rows<T>(dy, x, y, dx, dres, save_mean, save_rstd, gamma, coef, C, cv, r0, r1, tyi, ty, relu);
 }
 
+template <typename T>
+__global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_pdl_kernel(const T* __restrict__ dy, const T* __restrict__ x, const unsigned char* __restrict__ y,
+                                                                     T* __restrict__ dx, T* __restrict__ dres, const float* __restrict__ save_mean,
+                                                                     const float* __restrict__ save_rstd, const float* __restrict__ gamma,
+                                                                     const float* __restrict__ coef, int R, int C, int cvb, int ty, int relu) {
+  const int tx = threadIdx.x % cvb, tyi = threadIdx.x / cvb;
+  const int cv = blockIdx.x * cvb + tx;
+  const int S = gridDim.y;
+  const int rows_per = (R + S - 1) / S;
+  const int r0 = blockIdx.y * rows_per, r1 = min(R, r0 + rows_per);
+  bn_wait_producer();                               // coef / dgamma / dbeta come from the producer's last block
+  if (cv * kVec >= C) return;
+  bn_bwd_apply_rows<T>(dy, x, y, dx, dres, save_mean, save_rstd, gamma, coef, C, cv, r0, r1, tyi, ty, relu);
+}
+
+// B200DDP_PDL=1: stats -> apply and bwd_reduce -> bwd_apply become programmatic dependent launches
+int g_bn_pdl = -1;     // -1: read B200DDP_PDL on first use
+bool bn_pdl_enabled() {
+  if (g_bn_pdl < 0) { const char* e = getenv("B200DDP_PDL"); g_bn_pdl = (e && atoi(e) != 0) ? 1 : 0; }
+  return g_bn_pdl > 0;
+}
+
+template <typename... KArgs, typename... Args>
+void launch_dependent(void (*kernel)(KArgs...), dim3 grid, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kBnThreads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  B200_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+}
+
 Tile pick_tile(int R, int C) {
   Tile t;
   const int cv = C / kVec;
@@ -550,6 +609,8 @@ __global__ void __launch_bounds__(1024) bn_finish_partials_kernel(const float* _
   if (blockIdx.x == 0 && threadIdx.x == 0 && num_batches != nullptr) *num_batches += 1;
 }
 
+void set_bn_pdl(int on) { g_bn_pdl = on; }
+
 void bn_workspace_sizes(int R, int C, size_t* partial_floats, size_t* counters) {
   const Tile t = pick_tile(R, C);
   *partial_floats = (size_t)2 * t.grid_y * C;
@@ -566,6 +627,20 @@ void launch_bn_forward(const void* x, const void* residual, void* y, unsigned ch
   const size_t smem = (size_t)2 * t.ty * t.cvb * kVec * sizeof(float);
   const dim3 grid(t.grid_x, t.grid_y);
   const int r = relu ? 1 : 0;
+  if (!fused && bn_pdl_enabled()) {
+    // opt-in: producer with an early launch_dependents, apply kernel as its programmatic dependent
+#define B200_BN_FWD_PDL(T)                                                                                                                  \
+    bn_stats_kernel<T, false, true><<<grid, kBnThreads, smem, s>>>((const T*)x, R, C, t.cvb, t.ty, partial, counters, gamma, beta, running_mean, \
+                                                                   running_var, num_batches, save_mean, save_rstd, scale, shift, eps, momentum,  \
+                                                                   (const T*)residual, (T*)y, mask, r);                                          \
+    B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);                                                                                   \
+    launch_dependent(bn_apply_pdl_kernel<T>, apply_grid(t, R), s, (const T*)x, (const T*)residual, (T*)y, mask, (const float*)scale,              \
+                     (const float*)shift, R, C, t.cvb, t.ty, r);                                                                                  \
+    B200_COUNT_LAUNCH(1)
+    if (dt == DType::BF16) { B200_BN_FWD_PDL(__nv_bfloat16); } else { B200_BN_FWD_PDL(float); }
+#undef B200_BN_FWD_PDL
+    return;
+  }
 #define B200_BN_FWD(T, F)                                                                                                            \
   bn_stats_kernel<T, F><<<grid, kBnThreads, smem, s>>>((const T*)x, R, C, t.cvb, t.ty, partial, counters, gamma, beta, running_mean, \
                                                        running_var, num_batches, save_mean, save_rstd, scale, shift, eps, momentum, \
@@ -613,6 +688,19 @@ void launch_bn_backward(const void* dy, const void* x, const void* y, void* dx, 
   const size_t smem = (size_t)2 * t.ty * t.cvb * kVec * sizeof(float);
   const dim3 grid(t.grid_x, t.grid_y);
   const int r = relu ? 1 : 0;
+  if (!fused && bn_pdl_enabled()) {
+#define B200_BN_BWD_PDL(T)                                                                                                                    \
+    bn_bwd_reduce_kernel<T, false, true><<<grid, kBnThreads, smem, s>>>((const T*)dy, (const T*)x, (const unsigned char*)y, R, C, t.cvb, t.ty, r,  \
+                                                                        save_mean, save_rstd, partial, counters, dgamma, dbeta, coef, gamma,      \
+                                                                        (T*)dx, (T*)dres);                                                        \
+    B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);                                                                                     \
+    launch_dependent(bn_bwd_apply_pdl_kernel<T>, apply_grid(t, R), s, (const T*)dy, (const T*)x, (const unsigned char*)y, (T*)dx, (T*)dres,         \
+                     save_mean, save_rstd, gamma, (const float*)coef, R, C, t.cvb, t.ty, r);                                                        \
+    B200_COUNT_LAUNCH(1)
+    if (dt == DType::BF16) { B200_BN_BWD_PDL(__nv_bfloat16); } else { B200_BN_BWD_PDL(float); }
+#undef B200_BN_BWD_PDL
+    return;
+  }
 #define B200_BN_BWD(T, F)                                                                                                              \
   bn_bwd_reduce_kernel<T, F><<<grid, kBnThreads, smem, s>>>((const T*)dy, (const T*)x, (const unsigned char*)y, R, C, t.cvb, t.ty, r,  \
                                                             save_mean, save_rstd, partial, counters, dgamma, dbeta, coef, gamma,      \

@@ -160,7 +160,7 @@ def opt_ins(model):
     out = {}
     if int(getattr(model, "stem_pad_to", 0) or 0):
         out["stem_pad_channels"] = int(model.stem_pad_to)
-    for key in ("B200DDP_GEMM_GROUP_M", "B200DDP_GEMM_TMA_STORE", "B200DDP_GEMM_CTAS", "B200DDP_CONV1X1_TC", "B200DDP_CONV3X3_TC", "B200DDP_CONV_BN_FUSE", "B200DDP_BN_FUSED", "B200DDP_DISABLE_TC"):
+    for key in ("B200DDP_GEMM_GROUP_M", "B200DDP_GEMM_TMA_STORE", "B200DDP_GEMM_CTAS", "B200DDP_CONV1X1_TC", "B200DDP_CONV3X3_TC", "B200DDP_CONV_BN_FUSE", "B200DDP_BN_FUSED", "B200DDP_PDL", "B200DDP_DISABLE_TC"):
         if os.environ.get(key):
             out[key] = os.environ[key]
     return {"opt_in": out} if out else {}

@@ -173,3 +173,43 @@ def test_conv3x3_module_forward_and_dgrad_on_the_draft_kernel():
     def rel(u, v):
         return float((u.float() - v.float()).norm() / (v.float().norm() + 1e-12))
     assert rel(yb, ya) < 1e-2 and rel(xb.grad, xa.grad) < 1e-2 and rel(tc.weight.grad, ref.weight.grad) < 1e-2
+
+
+@pytest.mark.parametrize("shape", [(32, 64, 56, 56), (32, 1024, 14, 14), (8, 2048, 7, 7)])
+def test_batchnorm_programmatic_dependent_launch_is_bit_identical(shape):
+    """B200DDP_PDL: stats -> apply and bwd-reduce -> bwd-apply as programmatic dependent launches: same kernels' bodies,
+    same bits, eagerly and inside a captured CUDA graph."""
+    from b200ddp import _ext
+    from b200ddp.ops import FusedBatchNormAct2d
+    C = _ext.get()
+    torch.manual_seed(0)
+    x = torch.randn(*shape, device="cuda", dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    res = torch.randn_like(x)
+    g = torch.randn_like(x)
+
+    def run(pdl):
+        C.set_bn_pdl(pdl)
+        bn = FusedBatchNormAct2d(shape[1], relu=True).cuda()
+        xa = x.clone().requires_grad_(True)
+        y = bn(xa, residual=res)
+        y.backward(g)
+        return y.detach().clone(), xa.grad.clone(), bn.weight.grad.clone(), bn.running_var.clone()
+    try:
+        base = run(0)
+        pdl = run(1)
+        for a, b in zip(base, pdl):
+            assert torch.equal(a, b)
+        # under stream capture the dependent launch becomes a programmatic edge of the graph
+        bn = FusedBatchNormAct2d(shape[1], relu=True).cuda()
+        bn(x)                                             # allocate workspaces outside the capture
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = bn(x)
+        graph.replay()
+        torch.cuda.synchronize()
+        C.set_bn_pdl(0)
+        ref_bn = FusedBatchNormAct2d(shape[1], relu=True).cuda()
+        assert torch.equal(out, ref_bn(x))
+    finally:
+        C.set_bn_pdl(0)

@@ -29,6 +29,7 @@ run conv1x1_tc_tmastore_bnfuse B200DDP_CONV1X1_TC=1 B200DDP_GEMM_TMA_STORE=1 B20
 run conv1x1_tc_group8 B200DDP_CONV1X1_TC=1 B200DDP_GEMM_GROUP_M=8
 run stem_pad8_conv1x1 B200DDP_STEM_PAD=8 B200DDP_CONV1X1_TC=1
 run bn_fused B200DDP_BN_FUSED=1
+run bn_pdl B200DDP_PDL=1
 run conv3x3_tc B200DDP_CONV3X3_TC=1
 run all_conv_tc B200DDP_STEM_PAD=8 B200DDP_CONV1X1_TC=1 B200DDP_GEMM_TMA_STORE=1 B200DDP_CONV_BN_FUSE=1 B200DDP_CONV3X3_TC=1
 echo "== conv3x3 draft kernel vs cuDNN (time)"; timeout 300 python bench/conv_bench.py > $O/conv_bench.log 2>&1; echo "rc=$?"; cat $O/conv_bench.log
