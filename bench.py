@@ -402,10 +402,11 @@ def run_reference(args):
         sys.modules.pop(name, None)
     import ddp as ref          # noqa: E402  (reference ddp.py, unmodified)
     assert os.path.abspath(ref.__file__).startswith(ref_dir), ref.__file__
+    import torch.utils.data
     import torchvision
 
-    sys.path.append(ROOT)
-    from b200ddp.data.datasets import SyntheticImageNet, FooDataset as OurFoo   # data generator only
+    # nothing from this repository's package is imported in this arm: the data set below is the "user's dataset.py"
+    # (plain tensors + __getitem__), the model is stock torchvision, the loop / DDP / loader / optimizer are the reference's
 
     W, K = args.warmup, args.steps
     state = {"calls": 0, "t0": None, "t1": None, "h2d": 0}
@@ -449,9 +450,23 @@ def run_reference(args):
             x = inputs[0]
             state["h2d"] += x.numel() * x.element_size()
 
-    class RefDataset(SyntheticImageNet):
+    class RefDataset(torch.utils.data.Dataset):
+        """ImageNet-shaped synthetic samples with the dense one-hot target the reference's hard-coded MSELoss needs
+        (same generator, seed and shapes as b200ddp.data.SyntheticImageNet, re-stated here so this arm imports nothing of ours)."""
+
         def __init__(self, samples):   # the reference calls FooDataset(100000)
-            super().__init__(samples=args.samples, size=args.image_size, image_dtype=torch.float32, dense_target=True)
+            g = torch.Generator().manual_seed(1234)
+            n, size, classes = int(args.samples), int(args.image_size), 1000
+            self.X = torch.randn(n, 3, size, size, generator=g)
+            labels = torch.randint(0, classes, (n,), generator=g)
+            self.Y = torch.zeros(n, classes)
+            self.Y[torch.arange(n), labels] = 1.0
+
+        def __len__(self):
+            return self.X.shape[0]
+
+        def __getitem__(self, index):
+            return self.X[index], self.Y[index]
 
     if args.model != "foo":
         ref.FooDataset = RefDataset    # dataset.py is the template's customisation point; no source edit
