@@ -243,10 +243,15 @@ __global__ void __launch_bounds__(kCommThreads, kCommMinCtasPerSm) bucket_allred
   int hint = 0;
   constexpr int U = (sizeof(InT) == 4 && VE == 8) ? 2 : 4;    // independent vector requests in flight per thread and trip
 
-  // ---- phase 1: gather + scale + cast into local symmetric staging
-  for (int s = 0; s < (a.direct ? 0 : P); ++s) {
-    const uint32_t base_v = (uint32_t)s * Vs;
-    const uint32_t lim = min(Vs, V > base_v ? V - base_v : 0u);     // vectors of this slice that exist
+  // ---- phase 1: gather + scale + cast into local symmetric staging.
+  // Block ownership of a vector must be identical in every phase (the only cross-GPU synchronisation is block b <-> block b):
+  // the two-shot algorithms index every phase as slice_base + first + m * step, so they pack slice by slice; the one-shot
+  // algorithms read flat (first + m * step over [0, V)), so they pack flat too.
+  constexpr bool kFlat = (ALGO == kAlgoOneShot || ALGO == kAlgoNvlsOneShot);
+  const int pack_slices = a.direct ? 0 : (kFlat ? 1 : P);
+  for (int s = 0; s < pack_slices; ++s) {
+    const uint32_t base_v = kFlat ? 0u : (uint32_t)s * Vs;
+    const uint32_t lim = kFlat ? V : min(Vs, V > base_v ? V - base_v : 0u);     // vectors of this slice that exist
     for (uint32_t j = first; j < lim; j += U * step) {
       float f[U][VE];
 #pragma unroll

@@ -100,10 +100,11 @@ class Trainer:
 
         # ---- data ---------------------------------------------------------------------------------
         self.dataset = dataset if dataset is not None else build_dataset(args)
+        # one seedable, skippable sampler in every mode (single process = 1 replica), so mid-epoch resume replays nothing
         if self.distributed:
             self.sampler = ShardedSampler(self.dataset, seed=getattr(args, "sampler_seed", 0))
         else:
-            self.sampler = torch.utils.data.RandomSampler(self.dataset)
+            self.sampler = ShardedSampler(self.dataset, num_replicas=1, rank=0, seed=getattr(args, "sampler_seed", 0))
         self.loader = BatchLoader(self.dataset, batch_size=args.train_batch_size, sampler=self.sampler,
                                   pin_memory=self.device.type == "cuda")
         steps_per_epoch = len(self.loader) // args.gradient_accumulation_steps
@@ -217,13 +218,12 @@ class Trainer:
         if self.device.type == "cuda":
             torch.cuda.reset_peak_memory_stats(self.device)
         for epoch in trange(start_epoch, int(args.num_train_epochs), desc="Epoch", disable=not self.show_bars, leave=False):
-            if self.distributed:
-                self.sampler.set_epoch(epoch)
-                if skip_batches:
-                    self.sampler.set_start_index(skip_batches * args.train_batch_size)
+            self.sampler.set_epoch(epoch)
+            if skip_batches:
+                self.sampler.set_start_index(skip_batches * args.train_batch_size)
             feed = DevicePrefetcher(self.loader, self.device)
             with tqdm(feed, desc=f"Epoch {epoch}", disable=not self.show_bars, leave=False,
-                      total=len(self.loader) - (skip_batches if self.distributed else 0)) as bar:
+                      total=len(self.loader) - skip_batches) as bar:
                 for step, (x, y) in enumerate(bar):
                     self.model.train()
                     if x.device != self.device:
@@ -272,8 +272,8 @@ class Trainer:
         if self.device.type == "cuda":
             extra["peak_mem_gb"] = round(torch.cuda.max_memory_allocated(self.device) / 2 ** 30, 3)
         if self.last_throughput:
-            extra = {"ms_per_step": round(self.last_throughput["ms_per_step"], 4),
-                     "samples_per_s": round(self.last_throughput.get("samples_per_s", 0.0), 1)}
+            extra.update({"ms_per_step": round(self.last_throughput["ms_per_step"], 4),
+                          "samples_per_s": round(self.last_throughput.get("samples_per_s", 0.0), 1)})
         if hasattr(self.model, "ddp_stats"):
             extra["ddp"] = self.model.ddp_stats()
         log.info("Finished training.", dict(global_step=self.global_step, average_loss=total_loss / self.global_step,

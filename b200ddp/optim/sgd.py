@@ -85,7 +85,6 @@ class FusedSGD(torch.optim.Optimizer):
             blocks += g.plan.total_blocks
         self._own_partials = torch.zeros(max(blocks, 1), dtype=torch.float32, device=dev)
         self._lr_dev = torch.full((1,), float(self.param_groups[0]["lr"]), dtype=torch.float32, device=dev)
-        self._lr_pin = torch.empty(1, dtype=torch.float32).pin_memory()
         self._coef_dev = torch.ones(1, dtype=torch.float32, device=dev)
         self._norm_dev = torch.zeros(1, dtype=torch.float32, device=dev)
         self._step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -103,8 +102,10 @@ class FusedSGD(torch.optim.Optimizer):
     def sync_lr_to_device(self) -> None:
         """Called by the scheduler after it changes ``param_groups[0]['lr']``."""
         if self._native:
-            self._lr_pin[0] = float(self.param_groups[0]["lr"])
-            self._lr_dev.copy_(self._lr_pin, non_blocking=True)
+            # The value travels as a kernel argument, so it is bound at enqueue time: a host that runs several steps
+            # ahead of the GPU (prefetcher, graph replay) can never overwrite the lr of a step that has not executed yet
+            # (a single pinned staging word + async copy could).
+            self._lr_dev.fill_(float(self.param_groups[0]["lr"]))
 
     # ------------------------------------------------------------------ public API
     def clip_grad_norm_(self, max_norm: float) -> None:

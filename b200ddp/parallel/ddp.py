@@ -73,6 +73,8 @@ class _PyReducer:
         self._order_now: List[int] = []
 
     def mark_ready(self, pi: int) -> None:
+        if not self.active:        # second backward without an intervening forward: start a fresh pass, like Reducer::mark_ready
+            self.reset()
         b, k = self.where[pi]
         if self.fired[b][k]:
             raise RuntimeError(

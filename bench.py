@@ -62,6 +62,7 @@ def parse_args():
     p.add_argument("--gradient_as_bucket_view", action="store_true")
     p.add_argument("--find_unused_parameters", action="store_true")
     p.add_argument("--skip_e2e", action="store_true")
+    p.add_argument("--stock_graph", action="store_true", help="--impl stock: replay the whole stock step (fwd + bwd + DDP/NCCL + clip + SGD) from one CUDA graph")
     p.add_argument("--no_comm", action="store_true", help="diagnostic: N ranks, gradient communication disabled")
     p.add_argument("--profile_range", action="store_true", help="cudaProfilerStart/Stop around the device-timed loop (ncu --profile-from-start off)")
     args = p.parse_args()
@@ -78,7 +79,7 @@ class ClockSampler:
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int = 0):
+    def __init__(self, gpu_index=0):
         self.proc = None
         self.lines = []
         self.gpu_index = gpu_index
@@ -387,9 +388,14 @@ def run_reference(args):
         emit({"impl": "reference", "unavailable": "baseline/_ref is missing: run baseline/install_reference.sh"})
         return
     rank, local_rank, world = dist_env()
+    smi_index = str(local_rank)
     if args.gpus == 1 and "LOCAL_RANK" not in os.environ:
-        # the reference would otherwise wrap the model in DataParallel over every visible GPU (ddp.py:96-98,189-191)
-        os.environ.setdefault("CUDA_VISIBLE_DEVICES", "0")
+        # The reference would otherwise wrap the model in DataParallel over every visible GPU (ddp.py:96-98,189-191).
+        # Narrow visibility to ONE device whatever the incoming value is (on an 8-GPU box the variable may already list
+        # all eight, so setdefault was a no-op in round 1); must happen before torch initialises CUDA.
+        first = (os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")[0].strip()) or "0"
+        os.environ["CUDA_VISIBLE_DEVICES"] = first
+        smi_index = first                      # nvidia-smi -i takes the physical index or the UUID
     import torch
     import torch.nn as nn
     if not torch.cuda.is_available():
@@ -436,11 +442,13 @@ def run_reference(args):
             if world > 1:
                 torch.distributed.barrier(device_ids=[local_rank])
             torch.cuda.synchronize()
-            ev = torch.cuda.Event(enable_timing=True)
-            ev.record()
+            # both events on this process' training device (a DataParallel replica thread may have another one current)
+            with torch.cuda.device(ns.device if getattr(ns, "device", None) is not None and ns.device.type == "cuda" else torch.cuda.current_device()):
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
             state["t0" if idx == W else "t1"] = ev
             if idx == W:
-                state["clock"] = ClockSampler(local_rank if world > 1 else 0)
+                state["clock"] = ClockSampler(smi_index)
                 if rank == 0:
                     state["clock"].start()
             else:
@@ -518,6 +526,13 @@ def run_reference(args):
 # stock arm: plain torch DDP + NCCL + library kernels on the same workload (BASELINE configs 3 and 4)
 # --------------------------------------------------------------------------------------------------
 def run_stock(args):
+    """Competent stock loop (the honest bar next to the host-bound reference loop): torch DDP + NCCL + cuDNN/cuBLAS on
+    device-resident batches, bf16 autocast, clip + SGD every step; ``--stock_graph`` additionally captures the whole
+    step into one CUDA graph following torch's whole-network-capture recipe for DDP (side-stream construction, 11 eager
+    DDP iterations before capture, NCCL async error handling off)."""
+    if args.stock_graph:
+        os.environ["TORCH_NCCL_ASYNC_ERROR_HANDLING"] = "0"
+        os.environ["NCCL_ASYNC_ERROR_HANDLING"] = "0"
     import torch
     import torch.distributed as dist
     import torch.nn as nn
@@ -536,12 +551,16 @@ def run_stock(args):
     else:
         import torchvision
         model = getattr(torchvision.models, args.model)().to(dev).to(memory_format=torch.channels_last)
+    side = torch.cuda.Stream()
     if world > 1:
         kw = {}
         if args.bucket_cap_mb is not None:
             kw["bucket_cap_mb"] = args.bucket_cap_mb
-        model = nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], gradient_as_bucket_view=args.gradient_as_bucket_view,
-                                                    find_unused_parameters=args.find_unused_parameters, **kw)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            model = nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], gradient_as_bucket_view=args.gradient_as_bucket_view,
+                                                        find_unused_parameters=args.find_unused_parameters, **kw)
+        torch.cuda.current_stream().wait_stream(side)
     opt = torch.optim.SGD(model.parameters(), lr=1e-3)
     B = args.per_gpu_batch
     if is_bert:
@@ -551,8 +570,7 @@ def run_stock(args):
         xs = [torch.randn(B, 3, args.image_size, args.image_size, device=dev) for _ in range(4)]
         ys = [torch.zeros(B, 1000, device=dev) for _ in range(4)]
 
-    def one(i):
-        x, y = xs[i % 4], ys[i % 4]
+    def fwd_bwd_step(x, y):
         with torch.autocast("cuda", dtype=torch.bfloat16):
             if is_bert:
                 loss = model(input_ids=x, labels=y).loss
@@ -563,7 +581,33 @@ def run_stock(args):
         loss.backward()
         torch.nn.utils.clip_grad_norm_(model.parameters(), 1000.0)
         opt.step()
+
+    def one(i):
+        fwd_bwd_step(xs[i % 4], ys[i % 4])
         opt.zero_grad(set_to_none=True)
+
+    graph, graph_error = None, None
+    if args.stock_graph:
+        try:
+            sx, sy = xs[0].clone(), ys[0].clone()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for i in range(max(args.warmup, 12)):          # >= 11 DDP-enabled eager iterations before capture
+                    fwd_bwd_step(sx, sy)
+                    opt.zero_grad(set_to_none=True)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                fwd_bwd_step(sx, sy)
+            torch.cuda.synchronize()
+
+            def one(i):                                        # noqa: F811  (replay: copy the batch into the static buffers)
+                sx.copy_(xs[i % 4]); sy.copy_(ys[i % 4])
+                graph.replay()
+        except Exception as exc:
+            graph, graph_error = None, f"{type(exc).__name__}: {exc}"[:200]
+            raise SystemExit(f"stock CUDA-graph capture failed: {graph_error}")
 
     for i in range(max(args.warmup, 5)):
         one(i)
@@ -591,7 +635,9 @@ def run_stock(args):
               "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic, device-resident",
               "config": config_dict(args, world, {"transport": "nccl (stock torch DDP)", "bucket_cap_mb": args.bucket_cap_mb,
                                                   "gradient_as_bucket_view": args.gradient_as_bucket_view,
-                                                  "find_unused_parameters": args.find_unused_parameters})})
+                                                  "find_unused_parameters": args.find_unused_parameters,
+                                                  "cuda_graph": graph is not None, "amp": "torch.autocast bf16, fp32 params"})})
+
 
 def main():
     args = parse_args()
