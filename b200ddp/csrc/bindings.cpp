@@ -474,23 +474,69 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     return out;
   });
 
-  // ---- experimental: 3x3 convolution forward as nine shifted tcgen05 GEMMs (conv3x3_tcgen05.cu) -----
-  m.def("conv3x3_fwd", [](at::Tensor x, at::Tensor w) {
+  // ---- convolutions on tcgen05 (conv_tcgen05.cu / conv_wgrad_tcgen05.cu): channels_last bf16, stride 1, 1x1 or 3x3 ------
+  m.def("conv_fprop", [](at::Tensor x, at::Tensor w, int stride, int pad, int mode, int block_n, int base_offset, bool stats,
+                         c10::optional<at::Tensor> debug, int kc) {
     check_cuda(x, "x"); check_cuda(w, "w");
-    TORCH_CHECK(x.scalar_type() == at::kBFloat16 && w.scalar_type() == at::kBFloat16, "conv3x3_fwd: bf16 tensors");
-    TORCH_CHECK(x.dim() == 4 && x.is_contiguous(at::MemoryFormat::ChannelsLast), "conv3x3_fwd: x must be 4-D channels_last");
-    TORCH_CHECK(w.dim() == 4 && w.size(2) == 3 && w.size(3) == 3 && w.size(1) == x.size(1) && w.is_contiguous(at::MemoryFormat::ChannelsLast),
-                "conv3x3_fwd: filter must be [K, C, 3, 3] channels_last (stored [K][3][3][C])");
+    TORCH_CHECK(x.scalar_type() == at::kBFloat16 && w.scalar_type() == at::kBFloat16, "conv_fprop: bf16 tensors");
+    TORCH_CHECK(x.dim() == 4 && x.is_contiguous(at::MemoryFormat::ChannelsLast), "conv_fprop: x must be 4-D channels_last");
+    TORCH_CHECK(w.dim() == 4 && w.size(1) == x.size(1) && w.is_contiguous(at::MemoryFormat::ChannelsLast), "conv_fprop: filter must be [K, C, R, S] channels_last");
+    const int R = (int)w.size(2), S = (int)w.size(3);
+    TORCH_CHECK(stride == 1 && R == S && pad == (R - 1) / 2, "conv_fprop: stride 1, 'same' padding");
     c10::cuda::CUDAGuard guard(x.device());
     const int N = (int)x.size(0), C = (int)x.size(1), H = (int)x.size(2), W = (int)x.size(3), K = (int)w.size(0);
     at::Tensor y = at::empty({N, K, H, W}, x.options().memory_format(at::MemoryFormat::ChannelsLast));
-    launch_conv3x3_fprop(x.data_ptr(), w.data_ptr(), y.data_ptr(), N, H, W, C, K, cur_stream());
-    return y;
-  });
-  m.def("conv3x3_patch", [](int N, int H, int W) {
-    int bh = 0, bi = 0;
-    const bool ok = conv3x3_patch(N, H, W, &bh, &bi);
-    return std::make_tuple(ok, bh, bi);
+    ConvLaunchCfg cfg; cfg.mode = mode; cfg.block_n = block_n; cfg.set_base_offset = base_offset; cfg.kc = kc;
+    if (debug.has_value()) { TORCH_CHECK(debug->scalar_type() == at::kLong && debug->numel() >= 16 && debug->is_cuda(), "debug: int64[16] cuda"); cfg.debug_counters = debug->data_ptr(); }
+    at::Tensor st;
+    float* stp = nullptr;
+    if (stats) {
+      const int groups = conv_stat_groups(N, H, W, C, K, R, S, cfg);
+      TORCH_CHECK(groups > 0, "conv_fprop: no tile plan");
+      st = at::empty({2, groups, K}, x.options().dtype(at::kFloat));
+      stp = st.data_ptr<float>();
+    }
+    launch_conv_tap_gemm(x.data_ptr(), w.data_ptr(), y.data_ptr(), N, H, W, C, K, R, S, false, cfg, stp, cur_stream());
+    return std::make_tuple(y, st);
+  }, py::arg("x"), py::arg("w"), py::arg("stride") = 1, py::arg("pad") = 0, py::arg("mode") = -1, py::arg("block_n") = 0,
+     py::arg("base_offset") = 0, py::arg("stats") = false, py::arg("debug") = py::none(), py::arg("kc") = 0);
+  m.def("conv_dgrad", [](at::Tensor dy, at::Tensor w, int stride, int pad, int mode, int block_n, int base_offset, int kc) {
+    check_cuda(dy, "dy"); check_cuda(w, "w");
+    TORCH_CHECK(dy.scalar_type() == at::kBFloat16 && w.scalar_type() == at::kBFloat16, "conv_dgrad: bf16 tensors");
+    TORCH_CHECK(dy.dim() == 4 && dy.is_contiguous(at::MemoryFormat::ChannelsLast), "conv_dgrad: dy must be 4-D channels_last");
+    TORCH_CHECK(w.dim() == 4 && w.size(0) == dy.size(1) && w.is_contiguous(at::MemoryFormat::ChannelsLast), "conv_dgrad: filter must be [K, C, R, S] channels_last");
+    const int R = (int)w.size(2), S = (int)w.size(3);
+    TORCH_CHECK(stride == 1 && R == S && pad == (R - 1) / 2, "conv_dgrad: stride 1, 'same' padding");
+    c10::cuda::CUDAGuard guard(dy.device());
+    const int N = (int)dy.size(0), K = (int)dy.size(1), H = (int)dy.size(2), W = (int)dy.size(3), C = (int)w.size(1);
+    at::Tensor dx = at::empty({N, C, H, W}, dy.options().memory_format(at::MemoryFormat::ChannelsLast));
+    ConvLaunchCfg cfg; cfg.mode = mode; cfg.block_n = block_n; cfg.set_base_offset = base_offset; cfg.kc = kc;
+    launch_conv_tap_gemm(dy.data_ptr(), w.data_ptr(), dx.data_ptr(), N, H, W, C, K, R, S, true, cfg, nullptr, cur_stream());
+    return dx;
+  }, py::arg("dy"), py::arg("w"), py::arg("stride") = 1, py::arg("pad") = 0, py::arg("mode") = -1, py::arg("block_n") = 0,
+     py::arg("base_offset") = 0, py::arg("kc") = 0);
+  m.def("conv_wgrad", [](at::Tensor dy, at::Tensor x, int ksize, int stride, int pad, int split, int tile_m, int tile_n) {
+    check_cuda(dy, "dy"); check_cuda(x, "x");
+    TORCH_CHECK(dy.scalar_type() == at::kBFloat16 && x.scalar_type() == at::kBFloat16, "conv_wgrad: bf16 tensors");
+    TORCH_CHECK(dy.dim() == 4 && dy.is_contiguous(at::MemoryFormat::ChannelsLast) && x.dim() == 4 && x.is_contiguous(at::MemoryFormat::ChannelsLast),
+                "conv_wgrad: channels_last 4-D tensors");
+    TORCH_CHECK(stride == 1 && pad == (ksize - 1) / 2 && dy.size(0) == x.size(0) && dy.size(2) == x.size(2) && dy.size(3) == x.size(3),
+                "conv_wgrad: stride 1, 'same' padding");
+    c10::cuda::CUDAGuard guard(dy.device());
+    const int N = (int)x.size(0), C = (int)x.size(1), H = (int)x.size(2), W = (int)x.size(3), K = (int)dy.size(1);
+    WgradCfg cfg; cfg.split = split; cfg.tile_m = tile_m; cfg.tile_n = tile_n;
+    const size_t ws = conv_wgrad_workspace_floats(N, H, W, C, K, ksize, ksize, cfg);
+    TORCH_CHECK(ws > 0, "conv_wgrad: unsupported geometry / tiling");
+    at::Tensor work = at::empty({(int64_t)ws}, x.options().dtype(at::kFloat));
+    at::Tensor dw = at::empty({K, C, ksize, ksize}, x.options().memory_format(at::MemoryFormat::ChannelsLast));
+    launch_conv_wgrad(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), N, H, W, C, K, ksize, ksize, cfg, work.data_ptr<float>(), cur_stream());
+    return dw;
+  }, py::arg("dy"), py::arg("x"), py::arg("ksize"), py::arg("stride") = 1, py::arg("pad") = 0, py::arg("split") = 0,
+     py::arg("tile_m") = 0, py::arg("tile_n") = 0);
+  m.def("conv_tile_plan", [](int N, int H, int W, int R, int S, int mode) {
+    ConvTilePlan pl;
+    const bool ok = conv_tile_plan(N, H, W, R, S, mode, &pl);
+    return std::make_tuple(ok, pl.mode, pl.BH, pl.BI, pl.num_m_tiles, pl.dense_rows, pl.acc_rows, pl.a_rows);
   });
 
   // ---- fused BatchNorm ---------------------------------------------------------------------------

@@ -162,14 +162,11 @@ class Trainer:
         inv_std = torch.ones(3, device=self.device)
         scratch = {}
         cl = bool(getattr(self.args, "channels_last", False))
-        inner = getattr(self.model, "module", self.model)
-        pad_c = int(getattr(inner, "input_channels", 0) or 0) if cl else 0
 
         def transform(x):
             if x.dim() != 4 or x.dtype not in (torch.float32, torch.uint8) or not x.is_contiguous():
                 return x
-            # the model may ask for zero-padded channels (ResNet stem, see models/resnet.py::input_channels)
-            shape = (x.shape[0], max(int(x.shape[1]), pad_c), x.shape[2], x.shape[3])
+            shape = tuple(x.shape)
             dst = self.step_fn.static_inputs()[0]
             if dst is None or tuple(dst.shape) != shape or dst.dtype != self.compute_dtype:
                 dst = scratch.get(shape)

@@ -75,7 +75,7 @@ class FusedBatchNormAct2d(nn.BatchNorm2d):
     def forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None,
                 partials: Optional[torch.Tensor] = None) -> torch.Tensor:
         """``partials``: optional [2, groups, C] partial statistics of ``x`` from the kernel that produced it
-        (``functional.conv1x1_stats``); ignored on the stock fallback path, which recomputes them."""
+        (``functional.conv2d_tc``); ignored on the stock fallback path, which recomputes them."""
         if self._fusable(x) and (residual is None or (residual.dtype == x.dtype and residual.shape == x.shape)):
             if residual is not None and not residual.is_contiguous(memory_format=torch.channels_last):
                 residual = residual.contiguous(memory_format=torch.channels_last)

@@ -130,97 +130,78 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     return y
 
 
-def conv1x1(x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
-    """Pointwise (1x1, stride 1, no bias) convolution of a channels_last activation as ONE tcgen05 GEMM:
-    the NHWC tensor *is* the row-major [N*H*W, C_in] operand, the [C_out, C_in, 1, 1] filter the [C_out, C_in]
-    one, and the [N*H*W, C_out] result is the channels_last output - no im2col, no copies.  dgrad / wgrad reuse
-    ``_LinearTC``'s MN-major GEMMs.  Two thirds of ResNet-50's convolutions have this shape."""
-    n, c, h, w = x.shape
-    co = weight.shape[0]
-    ok = (x.is_cuda and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and weight.shape[2:] == (1, 1)
-          and x.is_contiguous(memory_format=torch.channels_last) and _tc_ok(n * h * w, co, c))
-    if not ok:
-        return F.conv2d(x, weight)
-    x2 = x.permute(0, 2, 3, 1).reshape(n * h * w, c)            # view of the NHWC storage
-    y2 = _LinearTC.apply(x2, weight.reshape(co, c), None, None)
-    return y2.view(n, h, w, co).permute(0, 3, 1, 2)             # channels_last-strided [N, C_out, H, W]
+# ------------------------------------------------------------------------------------------------
+# Convolutions on tcgen05 (csrc/conv_tcgen05.cu, csrc/conv_wgrad_tcgen05.cu)
+# ------------------------------------------------------------------------------------------------
+def _wgrad_native(cin: int, cout: int, k: int, pixels: int) -> bool:
+    """Which weight-gradient kernel runs: ours where it is at least level with the library per layer
+    (bench/conv_layers.py, profiles/conv_layers.md), the library's otherwise.  B200DDP_CONV_WGRAD=native|lib overrides."""
+    mode = os.environ.get("B200DDP_CONV_WGRAD", "auto")
+    if mode == "native":
+        return True
+    if mode == "lib":
+        return False
+    return k == 1 and pixels >= 25088 and not (cin == 64 and cout == 64)
 
 
-class _Conv1x1Stats(torch.autograd.Function):
-    """``_LinearTC`` without bias whose forward GEMM also emits the partial column statistics of its output
-    ([2, ceil(M/32), N] fp32: per-32-row sums and sums of squares) for the BatchNorm that follows."""
+def conv_tc_supported(x: torch.Tensor, weight: torch.Tensor, stride: int, padding: int) -> bool:
+    """stride-1 'same' 1x1 / 3x3 convolutions of channels_last bf16 CUDA tensors with channel counts that are multiples of 64."""
+    k = weight.shape[2]
+    return (x.is_cuda and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and x.dim() == 4 and stride == 1
+            and weight.shape[2] == weight.shape[3] and k in (1, 3) and padding == (k - 1) // 2
+            and x.shape[1] % 64 == 0 and weight.shape[0] % 64 == 0 and x.shape[3] + 2 <= 256
+            and os.environ.get("B200DDP_CONV", "native") != "lib")
+
+
+def _cl(t: torch.Tensor) -> torch.Tensor:
+    return t if t.is_contiguous(memory_format=torch.channels_last) else t.contiguous(memory_format=torch.channels_last)
+
+
+class _ConvTC(torch.autograd.Function):
+    """y = conv(x, w) (stride 1, 'same' padding) as a tcgen05 implicit GEMM; optionally also returns the per-CTA partial
+    column sums / sums of squares of y from the epilogue, so the BatchNorm that follows never re-reads y for its statistics.
+    Backward: data gradient on the same kernel (mirrored taps, filter read MN-major - no transposed weights), weight
+    gradient on the split-pixel tcgen05 kernel or the library (``_wgrad_native``)."""
 
     @staticmethod
-    def forward(ctx, x2, w2):
-        y2, partials = _C().gemm_stats(x2, w2)
-        ctx.save_for_backward(x2, w2)
-        ctx.mark_non_differentiable(partials)
-        return y2, partials
-
-    @staticmethod
-    def backward(ctx, dy, _dpartials):
+    def forward(ctx, x, w, want_stats):
         C = _C()
-        x2, w2 = ctx.saved_tensors
-        dy2 = dy if dy.is_contiguous() else dy.contiguous()
-        dx = C.gemm(dy2, w2, None, False, True, EPI_NONE, False, None) if ctx.needs_input_grad[0] else None
-        dw = C.gemm(dy2, x2, None, True, True, EPI_NONE, False, None) if ctx.needs_input_grad[1] else None
-        return dx, dw
-
-
-def conv1x1_stats(x: torch.Tensor, weight: torch.Tensor):
-    """``conv1x1`` that also returns the BatchNorm partial statistics computed in the GEMM epilogue (or ``None`` when
-    the tensor-core path does not apply and the caller should let BatchNorm compute its own)."""
-    n, c, h, w = x.shape
-    co = weight.shape[0]
-    ok = (x.is_cuda and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and weight.shape[2:] == (1, 1)
-          and x.is_contiguous(memory_format=torch.channels_last) and _tc_ok(n * h * w, co, c))
-    if not ok:
-        return F.conv2d(x, weight), None
-    x2 = x.permute(0, 2, 3, 1).reshape(n * h * w, c)
-    y2, partials = _Conv1x1Stats.apply(x2, weight.reshape(co, c))
-    return y2.view(n, h, w, co).permute(0, 3, 1, 2), partials
-
-
-# ------------------------------------------------------------------------------------------------
-# 3x3 convolution (experimental, opt-in): forward and dgrad on the nine-shifted-GEMM kernel
-# ------------------------------------------------------------------------------------------------
-def _conv3x3_fprop(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
-    """stride-1 / pad-1 3x3 convolution: ``csrc/conv3x3_tcgen05.cu`` for channels_last bf16 CUDA tensors it covers,
-    the stock op otherwise (CPU tests exercise the surrounding autograd logic through this fallback)."""
-    if (x.is_cuda and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and x.shape[1] % 64 == 0 and w.shape[0] % 8 == 0
-            and x.shape[3] <= 128):
-        xc = x if x.is_contiguous(memory_format=torch.channels_last) else x.contiguous(memory_format=torch.channels_last)
-        wc = w if w.is_contiguous(memory_format=torch.channels_last) else w.contiguous(memory_format=torch.channels_last)
-        return _C().conv3x3_fwd(xc, wc)
-    return F.conv2d(x, w, padding=1)
-
-
-class _Conv3x3TC(torch.autograd.Function):
-    """fprop and dgrad are the same kernel: dx = conv3x3(dy, W') with W'[ci, co, r, s] = W[co, ci, 2-r, 2-s] (a
-    few-hundred-KB permutation per layer); wgrad stays on the library (``aten::convolution_backward``) until the split-K
-    tcgen05 version exists."""
+        xc, wc = _cl(x), _cl(w)
+        k = w.shape[2]
+        y, st = C.conv_fprop(xc, wc, 1, (k - 1) // 2, -1, 0, 0, bool(want_stats))
+        ctx.save_for_backward(xc, wc)
+        ctx.k = k
+        ctx.w_strides = w.stride()
+        if want_stats:
+            ctx.mark_non_differentiable(st)
+            return y, st
+        return y, None
 
     @staticmethod
-    def forward(ctx, x, w):
-        ctx.save_for_backward(x, w)
-        return _conv3x3_fprop(x, w)
-
-    @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, _dstats):
+        C = _C()
         x, w = ctx.saved_tensors
+        k = ctx.k
+        pad = (k - 1) // 2
+        dyc = _cl(dy)
         dx = dw = None
         if ctx.needs_input_grad[0]:
-            w_t = w.flip(2, 3).transpose(0, 1)
-            dx = _conv3x3_fprop(dy, w_t.contiguous(memory_format=torch.channels_last) if w.is_cuda else w_t)
+            dx = C.conv_dgrad(dyc, w, 1, pad, -1, 0, 0)
         if ctx.needs_input_grad[1]:
-            dw = torch.ops.aten.convolution_backward(dy, x, w, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1,
-                                                     [False, True, False])[1]
-        return dx, dw
+            n, cin, h, wd = x.shape
+            if _wgrad_native(cin, w.shape[0], k, n * h * wd):
+                dw = C.conv_wgrad(dyc, x, k, 1, pad, 0, 0, 0)
+            else:
+                dw = torch.ops.aten.convolution_backward(dyc, x, w, None, [1, 1], [pad, pad], [1, 1], False, [0, 0], 1,
+                                                         [False, True, False])[1]
+            if k == 1 and tuple(dw.stride()) != tuple(ctx.w_strides):
+                dw = dw.as_strided(dw.shape, ctx.w_strides)      # same memory order; match the parameter's strides so autograd steals it
+        return dx, dw, None
 
 
-def conv3x3(x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
-    """3x3, stride 1, zero padding 1, no bias."""
-    return _Conv3x3TC.apply(x, weight)
+def conv2d_tc(x: torch.Tensor, weight: torch.Tensor, want_stats: bool = False):
+    """(y, partial BatchNorm statistics or None).  Caller checks ``conv_tc_supported`` first."""
+    return _ConvTC.apply(x, weight, want_stats)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -37,44 +37,38 @@ class Linear(nn.Module):
         return f"in={self.in_features}, out={self.out_features}, bias={self.bias is not None}, act={self.activation}"
 
 
-class PointwiseConv2d(nn.Conv2d):
-    """1x1 bias-free ``nn.Conv2d`` (same parameter name, shape and init).  Default: cuDNN, exactly like
-    ``nn.Conv2d``.  Opt-in (``B200DDP_CONV1X1_TC=1`` at construction, or ``use_tc=True``): stride-1 instances
-    run fprop / dgrad / wgrad on the tcgen05 GEMM (``functional.conv1x1``)."""
+class Conv2dTC(nn.Conv2d):
+    """Bias-free ``nn.Conv2d`` (same parameter name, shape and init, so checkpoints and DDP bucket layouts are unchanged)
+    whose stride-1 1x1 / 3x3 instances run forward, data gradient and (where it wins) weight gradient on the hand-written
+    tcgen05 kernels for channels_last bf16 CUDA tensors; everything else (CPU, fp32, stride 2, odd channel counts) takes
+    the stock path.  ``forward_with_stats`` additionally hands the following BatchNorm its statistics from the epilogue."""
 
-    def __init__(self, in_channels: int, out_channels: int, stride: int = 1, use_tc: Optional[bool] = None, **kw):
-        super().__init__(in_channels, out_channels, 1, stride=stride, bias=False, **kw)
-        if use_tc is None:
-            use_tc = os.environ.get("B200DDP_CONV1X1_TC", "0") == "1"
-        self.use_tc = bool(use_tc) and self.stride == (1, 1)
+    def __init__(self, in_channels: int, out_channels: int, kernel_size: int = 1, stride: int = 1, **kw):
+        super().__init__(in_channels, out_channels, kernel_size, stride=stride, padding=(kernel_size - 1) // 2, bias=False, **kw)
+
+    def _native(self, x: torch.Tensor) -> bool:
+        return Fn.conv_tc_supported(x, self.weight, self.stride[0], self.padding[0]) and self.stride[0] == self.stride[1]
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        if self.use_tc and x.is_cuda:
-            return Fn.conv1x1(x, self.weight)
+        if self._native(x):
+            return Fn.conv2d_tc(x, self.weight, False)[0]
         return super().forward(x)
 
     def forward_with_stats(self, x: torch.Tensor):
-        """(y, partial BatchNorm statistics from the GEMM epilogue) - statistics are ``None`` off the tensor-core path."""
-        if self.use_tc and x.is_cuda:
-            return Fn.conv1x1_stats(x, self.weight)
+        """(y, partial BatchNorm statistics [2, G, C_out] from the convolution's epilogue, or None on the stock path)."""
+        if self._native(x):
+            return Fn.conv2d_tc(x, self.weight, True)
         return super().forward(x), None
 
 
-class Conv3x3(nn.Conv2d):
-    """3x3 / pad 1 bias-free ``nn.Conv2d`` (same parameter name, shape, init).  Default: cuDNN.  Opt-in
-    (``B200DDP_CONV3X3_TC=1`` at construction, or ``use_tc=True``): stride-1 instances run forward and dgrad on the
-    experimental nine-shifted-GEMM tcgen05 kernel (``functional.conv3x3``)."""
+class PointwiseConv2d(Conv2dTC):
+    def __init__(self, in_channels: int, out_channels: int, stride: int = 1, **kw):
+        super().__init__(in_channels, out_channels, 1, stride=stride, **kw)
 
-    def __init__(self, in_channels: int, out_channels: int, stride: int = 1, use_tc: Optional[bool] = None, **kw):
-        super().__init__(in_channels, out_channels, 3, stride=stride, padding=1, bias=False, **kw)
-        if use_tc is None:
-            use_tc = os.environ.get("B200DDP_CONV3X3_TC", "0") == "1"
-        self.use_tc = bool(use_tc) and self.stride == (1, 1)
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
-        if self.use_tc:
-            return Fn.conv3x3(x, self.weight)
-        return super().forward(x)
+class Conv3x3(Conv2dTC):
+    def __init__(self, in_channels: int, out_channels: int, stride: int = 1, **kw):
+        super().__init__(in_channels, out_channels, 3, stride=stride, **kw)
 
 
 class LayerNorm(nn.Module):

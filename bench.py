@@ -156,12 +156,10 @@ def make_dataset(args):
 
 
 def opt_ins(model):
-    """Non-default kernel paths switched on through the environment (none by default) - recorded so a run is
+    """Non-default kernel choices switched on through the environment (none by default) - recorded so a run is
     reproducible from its JSON line."""
     out = {}
-    if int(getattr(model, "stem_pad_to", 0) or 0):
-        out["stem_pad_channels"] = int(model.stem_pad_to)
-    for key in ("B200DDP_GEMM_GROUP_M", "B200DDP_GEMM_TMA_STORE", "B200DDP_GEMM_CTAS", "B200DDP_CONV1X1_TC", "B200DDP_CONV3X3_TC", "B200DDP_CONV_BN_FUSE", "B200DDP_BN_FUSED", "B200DDP_PDL", "B200DDP_DISABLE_TC"):
+    for key in ("B200DDP_GEMM_GROUP_M", "B200DDP_GEMM_TMA_STORE", "B200DDP_GEMM_CTAS", "B200DDP_CONV", "B200DDP_CONV_WGRAD", "B200DDP_DISABLE_TC"):
         if os.environ.get(key):
             out[key] = os.environ[key]
     return {"opt_in": out} if out else {}
@@ -237,8 +235,7 @@ def run_ours(args):
     def input_transform(x):
         if not is_image:
             return x if x.dtype == compute_dtype or not x.is_floating_point() else x.to(compute_dtype)
-        # B200DDP_STEM_PAD (opt-in) makes the model ask for zero-padded input channels; default: same shape as x
-        shape = (x.shape[0], max(int(x.shape[1]), int(getattr(inner, "input_channels", 0) or 0)), x.shape[2], x.shape[3])
+        shape = tuple(x.shape)
         buf = step.static_inputs()[0]          # after capture: write straight into the graph's input buffer
         if buf is None or tuple(buf.shape) != shape:
             buf = static_in.get("x")

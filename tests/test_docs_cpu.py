@@ -3,7 +3,7 @@ import os
 import re
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-DOCS = ["README.md", "DESIGN.md", "docs/INVENTORY.md", "docs/ROADMAP.md", "docs/MIGRATING.md", "profiles/README.md"]
+DOCS = ["README.md", "DESIGN.md", "docs/INVENTORY.md", "docs/MIGRATING.md", "profiles/README.md"]
 
 
 def _read(rel):

@@ -1,0 +1,115 @@
+"""tcgen05 convolution kernels (csrc/conv_tcgen05.cu, csrc/conv_wgrad_tcgen05.cu) against a plain PyTorch fp32 reference of
+the same op: forward, data gradient, weight gradient, epilogue BatchNorm statistics, every tiling, ResNet's map sizes."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return float((a.float() - b.float()).norm() / (b.float().norm() + 1e-12))
+
+
+def _mk(n, ci, co, k, h, w):
+    torch.manual_seed(n * 1000 + ci + co + k + h)
+    dev = "cuda"
+    x = torch.randn(n, ci, h, w, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    wt = (torch.randn(co, ci, k, k, device=dev) / (ci * k * k) ** 0.5).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    dy = torch.randn(n, co, h, w, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    return x, wt, dy
+
+
+def _ref(x, wt, dy, k):
+    xf = x.float().requires_grad_(True)
+    wf = wt.float().requires_grad_(True)
+    y = F.conv2d(xf, wf, padding=(k - 1) // 2)
+    y.backward(dy.float())
+    return y.detach(), xf.grad, wf.grad
+
+
+SHAPES = [  # n, cin, cout, k, h, w
+    (4, 64, 64, 1, 56, 56), (2, 256, 64, 1, 56, 56), (3, 64, 256, 1, 28, 28), (5, 512, 128, 1, 14, 14), (6, 128, 512, 1, 7, 7),
+    (1, 2048, 512, 1, 7, 7), (2, 64, 64, 3, 56, 56), (3, 128, 128, 3, 28, 28), (4, 256, 256, 3, 14, 14), (6, 512, 512, 3, 7, 7),
+    (2, 64, 128, 3, 9, 12), (1, 64, 64, 1, 5, 3),
+]
+
+
+@pytest.mark.parametrize("n,ci,co,k,h,w", SHAPES)
+def test_forward_and_data_gradient_match_fp32_reference(n, ci, co, k, h, w):
+    from b200ddp import _ext
+    C = _ext.get()
+    x, wt, dy = _mk(n, ci, co, k, h, w)
+    y_ref, dx_ref, _ = _ref(x, wt, dy, k)
+    pad = (k - 1) // 2
+    modes = [-1] if k == 1 else [1, 2]
+    for mode in modes:
+        for bn in (0, 64, 128, 256):
+            if bn and (co % bn or ci % bn):
+                continue
+            y = C.conv_fprop(x, wt, 1, pad, mode, bn, 0, False)[0]
+            dx = C.conv_dgrad(dy, wt, 1, pad, mode, bn, 0)
+            assert y.shape == y_ref.shape and y.is_contiguous(memory_format=torch.channels_last)
+            assert _rel(y, y_ref) < 6e-3, (mode, bn, _rel(y, y_ref))
+            assert _rel(dx, dx_ref) < 6e-3, (mode, bn, _rel(dx, dx_ref))
+
+
+@pytest.mark.parametrize("n,ci,co,k,h,w", SHAPES)
+def test_weight_gradient_matches_fp32_reference(n, ci, co, k, h, w):
+    from b200ddp import _ext
+    C = _ext.get()
+    x, wt, dy = _mk(n, ci, co, k, h, w)
+    _, _, dw_ref = _ref(x, wt, dy, k)
+    pad = (k - 1) // 2
+    for (split, tm, tn) in [(0, 0, 0), (1, 0, 0), (3, 128, 64)]:
+        dw = C.conv_wgrad(dy, x, k, 1, pad, split, tm, tn)
+        assert dw.shape == dw_ref.shape
+        assert _rel(dw, dw_ref) < 6e-3, (split, tm, tn, _rel(dw, dw_ref))
+    # deterministic: fixed-order reduction of the split partials
+    a = C.conv_wgrad(dy, x, k, 1, pad, 0, 0, 0)
+    b = C.conv_wgrad(dy, x, k, 1, pad, 0, 0, 0)
+    assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("n,ci,co,k,h,w", [(4, 64, 256, 1, 56, 56), (3, 256, 128, 1, 28, 28), (2, 64, 64, 3, 56, 56), (5, 256, 256, 3, 14, 14),
+                                           (7, 512, 2048, 1, 7, 7)])
+def test_epilogue_statistics_equal_the_column_sums_of_the_stored_output(n, ci, co, k, h, w):
+    from b200ddp import _ext
+    C = _ext.get()
+    x, wt, _ = _mk(n, ci, co, k, h, w)
+    y, st = C.conv_fprop(x, wt, 1, (k - 1) // 2, -1, 0, 0, True)
+    assert st.shape[0] == 2 and st.shape[2] == co
+    y2 = y.permute(0, 2, 3, 1).reshape(-1, co).float()
+    s, q = st[0].sum(0), st[1].sum(0)
+    assert torch.allclose(s, y2.sum(0), rtol=2e-3, atol=2e-2 * float(y2.abs().sum(0).max()) / y2.shape[0] + 1e-2)
+    assert torch.allclose(q, (y2 * y2).sum(0), rtol=2e-3, atol=1e-2)
+    # identical output with and without the statistics epilogue, and run to run
+    assert torch.equal(y, C.conv_fprop(x, wt, 1, (k - 1) // 2, -1, 0, 0, False)[0])
+    assert torch.equal(st, C.conv_fprop(x, wt, 1, (k - 1) // 2, -1, 0, 0, True)[1])
+
+
+def test_bottleneck_matches_stock_modules_forward_and_backward():
+    """Conv2dTC + FusedBatchNormAct2d with statistics from the epilogue vs nn.Conv2d + nn.BatchNorm2d in fp32."""
+    import torch.nn as nn
+    from b200ddp.models.resnet import Bottleneck
+    from b200ddp.utils import to_mixed_bf16
+    torch.manual_seed(0)
+    blk = to_mixed_bf16(Bottleneck(256, 64).cuda()).to(memory_format=torch.channels_last)
+    ref = nn.Sequential(nn.Conv2d(256, 64, 1, bias=False), nn.BatchNorm2d(64), nn.ReLU(), nn.Conv2d(64, 64, 3, padding=1, bias=False), nn.BatchNorm2d(64),
+                        nn.ReLU(), nn.Conv2d(64, 256, 1, bias=False), nn.BatchNorm2d(256)).cuda()
+    with torch.no_grad():
+        for a, b in ((blk.conv1, ref[0]), (blk.conv2, ref[3]), (blk.conv3, ref[6])):
+            b.weight.copy_(a.weight.float())
+    x = torch.randn(8, 256, 28, 28, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    xr = x.detach().float().requires_grad_(True)
+    y = blk(x)
+    yr = torch.relu(ref(xr) + xr)
+    assert _rel(y, yr) < 3e-2
+    g = torch.randn_like(yr)
+    y.backward(g.to(torch.bfloat16).contiguous(memory_format=torch.channels_last))
+    yr.backward(g)
+    assert _rel(x.grad, xr.grad) < 6e-2
+    for a, b in ((blk.conv1, ref[0]), (blk.conv2, ref[3]), (blk.conv3, ref[6])):
+        assert _rel(a.weight.grad, b.weight.grad) < 1e-1      # bf16 activations through three BatchNorms vs an fp32 chain
+        assert a.weight.grad.stride() == a.weight.stride()
+    assert torch.allclose(blk.bn1.running_mean, ref[1].running_mean, atol=2e-2)
