@@ -132,24 +132,18 @@ def test_static_loss_scale_is_transparent():
         assert torch.allclose(p, q, atol=1e-6)
 
 
-def test_resnet_stem_channel_padding_is_transparent():
-    """Opt-in stem padding (zero channels + zero taps appended) is the same function with the same parameters."""
+def test_resnet_matches_torchvision_given_its_weights():
+    """Same parameter names / shapes as torchvision's ResNet-50 (checkpoints and DDP bucket layouts carry over) and, on the
+    stock CPU path, the same function."""
     import torch
+    tv = pytest.importorskip("torchvision")
     from b200ddp.models.resnet import ResNet
     torch.manual_seed(0)
-    a = ResNet([1, 1, 1, 1], num_classes=10)
-    b = ResNet([1, 1, 1, 1], num_classes=10, stem_pad_to=8)
-    b.load_state_dict(a.state_dict())                     # identical parameter names and shapes
-    assert a.input_channels == 3 and b.input_channels == 8
+    ref = tv.models.resnet.ResNet(tv.models.resnet.Bottleneck, [1, 1, 1, 1], num_classes=10)
+    ours = ResNet([1, 1, 1, 1], num_classes=10)
+    ours.load_state_dict(ref.state_dict())                # identical parameter / buffer names and shapes
     x = torch.randn(2, 3, 64, 64)
-    ya, yb = a(x), b(x)
-    assert torch.allclose(ya, yb, atol=1e-5)
-    xp = torch.cat([x, torch.zeros(2, 5, 64, 64)], 1)     # what the fused input kernel emits
-    assert torch.allclose(b(xp), ya, atol=1e-5)
-    ya.square().mean().backward()
-    yb.square().mean().backward()
-    assert torch.allclose(a.conv1.weight.grad, b.conv1.weight.grad, atol=1e-6)
-    assert b.conv1.weight.grad.shape == (64, 3, 7, 7)
+    assert torch.allclose(ours(x), ref(x), atol=1e-4)
 
 
 def test_bert_matches_huggingface_reference_given_its_weights():
