@@ -291,6 +291,11 @@ __device__ __forceinline__ void bn_bwd_apply_rows(const T* __restrict__ dy, cons
                                                   T* __restrict__ dx, T* __restrict__ dres, const float* __restrict__ save_mean,
                                                   const float* __restrict__ save_rstd, const float* __restrict__ gamma,
                                                   const float* __restrict__ coef, int C, int cv, int r0, int r1, int tyi, int ty, int relu);
+template <typename T>
+__device__ __forceinline__ void bn_bwd_apply_rows_coef(const T* __restrict__ dy, const T* __restrict__ x, const unsigned char* __restrict__ y,
+                                                       T* __restrict__ dx, T* __restrict__ dres, const float* __restrict__ save_mean,
+                                                       const float* __restrict__ save_rstd, const float* __restrict__ gamma,
+                                                       const float* c1p, const float* c2p, int C, int cv, int r0, int r1, int tyi, int ty, int relu);
 
 // ------------------------------------------------------------------------------------------------------
 template <typename T, bool FUSED, bool PDL = false>
@@ -410,11 +415,12 @@ __global__ void __launch_bounds__(kBnThreads, 2) bn_bwd_reduce_kernel(const T* _
   if (cv * kVec < C) bn_bwd_apply_rows<T>(dy, x, y, dx, dres, save_mean, save_rstd, gamma, coef, C, cv, r0, r1, tyi, ty, relu);
 }
 
+// c1p / c2p point at THIS thread's 8 coefficients (global coef rows or a block's shared-memory copy)
 template <typename T>
-__device__ __forceinline__ void bn_bwd_apply_rows(const T* __restrict__ dy, const T* __restrict__ x, const unsigned char* __restrict__ y,
-                                                  T* __restrict__ dx, T* __restrict__ dres, const float* __restrict__ save_mean,
-                                                  const float* __restrict__ save_rstd, const float* __restrict__ gamma,
-                                                  const float* __restrict__ coef, int C, int cv, int r0, int r1, int tyi, int ty, int relu) {
+__device__ __forceinline__ void bn_bwd_apply_rows_coef(const T* __restrict__ dy, const T* __restrict__ x, const unsigned char* __restrict__ y,
+                                                       T* __restrict__ dx, T* __restrict__ dres, const float* __restrict__ save_mean,
+                                                       const float* __restrict__ save_rstd, const float* __restrict__ gamma,
+                                                       const float* c1p, const float* c2p, int C, int cv, int r0, int r1, int tyi, int ty, int relu) {
   // dx = a*dy* + b*x + c  with per-channel a = gamma*rstd, b = -a*rstd*c2, c = -a*(c1 - mean*rstd*c2)
   float ka[kVec], kb[kVec], kc[kVec];
   {
@@ -422,8 +428,8 @@ __device__ __forceinline__ void bn_bwd_apply_rows(const T* __restrict__ dy, cons
     bn_load8<float>(save_mean + cv * kVec, mean);
     bn_load8<float>(save_rstd + cv * kVec, rstd);
     bn_load8<float>(gamma + cv * kVec, gam);
-    bn_load8<float>(coef + cv * kVec, c1);
-    bn_load8<float>(coef + C + cv * kVec, c2);
+    bn_load8<float>(c1p, c1);
+    bn_load8<float>(c2p, c2);
 #pragma unroll
     for (int i = 0; i < kVec; ++i) {
       ka[i] = gam[i] * rstd[i];
@@ -470,6 +476,14 @@ __device__ __forceinline__ void bn_bwd_apply_rows(const T* __restrict__ dy, cons
     if (dres != nullptr) bn_store8<T>(dres + off, g);
     bn_store8<T>(dx + off, o);
   }
+}
+
+template <typename T>
+__device__ __forceinline__ void bn_bwd_apply_rows(const T* __restrict__ dy, const T* __restrict__ x, const unsigned char* __restrict__ y,
+                                                  T* __restrict__ dx, T* __restrict__ dres, const float* __restrict__ save_mean,
+                                                  const float* __restrict__ save_rstd, const float* __restrict__ gamma,
+                                                  const float* __restrict__ coef, int C, int cv, int r0, int r1, int tyi, int ty, int relu) {
+  bn_bwd_apply_rows_coef<T>(dy, x, y, dx, dres, save_mean, save_rstd, gamma, coef + cv * kVec, coef + C + cv * kVec, C, cv, r0, r1, tyi, ty, relu);
 }
 
 template <typename T>
@@ -564,49 +578,121 @@ bool fused_tile(int R, int C, Tile* t) {
 
 }  // namespace
 
-// Statistics from partial sums produced elsewhere ([2][G][C]: per-row-group column sums / sums of squares written by
-// the tcgen05 GEMM epilogue of the producing 1x1 convolution): 32 channels per block, 32 row-lanes per channel, fixed
-// summation order -> deterministic.  Same outputs as the finish step of bn_stats_kernel.
-__global__ void __launch_bounds__(1024) bn_finish_partials_kernel(const float* __restrict__ partial, int G, int C, int R,
-                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                                  float* __restrict__ running_mean, float* __restrict__ running_var,
-                                                                  long long* __restrict__ num_batches, float* __restrict__ save_mean,
-                                                                  float* __restrict__ save_rstd, float* __restrict__ scale,
-                                                                  float* __restrict__ shift, float eps, float momentum) {
-  __shared__ float ssum[32][33], ssq[32][33];
-  const int tx = threadIdx.x & 31, l = threadIdx.x >> 5;
-  const int ch = blockIdx.x * 32 + tx;
-  float ps = 0.f, pq = 0.f;
-  if (ch < C) {
-#pragma unroll 4
-    for (int k = l; k < G; k += 32) {
-      ps += __ldcg(&partial[(size_t)k * C + ch]);
-      pq += __ldcg(&partial[((size_t)G + k) * C + ch]);
-    }
-  }
-  ssum[l][tx] = ps;
-  ssq[l][tx] = pq;
-  __syncthreads();
-  if (l == 0 && ch < C) {
-    float s = 0.f, q = 0.f;
+// ------------------------------------------------------------------------------------------------------
+// Statistics from the producing convolution's epilogue (csrc/conv_tcgen05.cu): partial = [2][G][C] per-CTA column sums and
+// sums of squares, G <= 148.  NO separate finishing launch: every block of the normalisation kernel first reduces the G
+// rows of ITS <= 64 channels (a few tens of KB out of L2, fixed order -> deterministic), then normalises its rows; the
+// blocks of the first row split also publish mean / rstd (for the backward pass) and update the running statistics.
+template <typename T>
+__global__ void __launch_bounds__(kBnThreads) bn_apply_partials_kernel(const T* __restrict__ x, const T* __restrict__ residual, T* __restrict__ y,
+                                                                      unsigned char* __restrict__ mask, const float* __restrict__ partial, int G,
+                                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                      float* __restrict__ running_mean, float* __restrict__ running_var,
+                                                                      long long* __restrict__ num_batches, float* __restrict__ save_mean,
+                                                                      float* __restrict__ save_rstd, float eps, float momentum, int R, int C,
+                                                                      int cvb, int ty, int relu) {
+  extern __shared__ float bn_smem[];                 // [2][ty][cvb*8] reduction scratch, then [2][cvb*8] scale / shift
+  const int tx = threadIdx.x % cvb, tyi = threadIdx.x / cvb;
+  const int cv = blockIdx.x * cvb + tx;
+  const bool live = cv * kVec < C;
+  float acc[2][kVec];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) { s += ssum[i][tx]; q += ssq[i][tx]; }
-    const float inv_r = 1.f / (float)R;
-    const float mean = s * inv_r;
-    const float var = fmaxf(q * inv_r - mean * mean, 0.f);
-    const float rstd = rsqrtf(var + eps);
-    const float sc = gamma[ch] * rstd;
-    save_mean[ch] = mean;
-    save_rstd[ch] = rstd;
-    scale[ch] = sc;
-    shift[ch] = beta[ch] - mean * sc;
-    if (running_mean != nullptr) {
-      const float unbiased = R > 1 ? var * ((float)R / (float)(R - 1)) : var;
-      running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * mean;
-      running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * unbiased;
+  for (int i = 0; i < kVec; ++i) { acc[0][i] = 0.f; acc[1][i] = 0.f; }
+  if (live) {
+    for (int g = tyi; g < G; g += ty) {
+      float a[kVec], b[kVec];
+      bn_load8<float>(partial + (size_t)g * C + cv * kVec, a);
+      bn_load8<float>(partial + ((size_t)G + g) * C + cv * kVec, b);
+#pragma unroll
+      for (int i = 0; i < kVec; ++i) { acc[0][i] += a[i]; acc[1][i] += b[i]; }
     }
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0 && num_batches != nullptr) *num_batches += 1;
+  reduce_rows<2>(acc, bn_smem, tx, tyi, cvb, ty);
+  const int width = cvb * kVec;
+  float* sc_s = bn_smem + 2 * ty * width;            // scale / shift of this block's channels
+  float* sh_s = sc_s + width;
+  if (tyi == 0 && live) {
+    const float inv_r = 1.f / (float)R;
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) {
+      const int ch = cv * kVec + i;
+      const float sum = bn_smem[tx * kVec + i], sq = bn_smem[ty * width + tx * kVec + i];
+      const float mean = sum * inv_r;
+      const float var = fmaxf(sq * inv_r - mean * mean, 0.f);
+      const float rstd = rsqrtf(var + eps);
+      const float sc = gamma[ch] * rstd;
+      sc_s[tx * kVec + i] = sc;
+      sh_s[tx * kVec + i] = beta[ch] - mean * sc;
+      if (blockIdx.y == 0) {
+        save_mean[ch] = mean;
+        save_rstd[ch] = rstd;
+        if (running_mean != nullptr) {
+          const float unbiased = R > 1 ? var * ((float)R / (float)(R - 1)) : var;
+          running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * mean;
+          running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * unbiased;
+        }
+      }
+    }
+  }
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && num_batches != nullptr) *num_batches += 1;
+  __syncthreads();
+  if (!live) return;
+  const int S = gridDim.y;
+  const int rows_per = (R + S - 1) / S;
+  const int r0 = blockIdx.y * rows_per, r1 = min(R, r0 + rows_per);
+  // bn_apply_rows indexes scale / shift by the global channel vector: hand it pointers rebased to this block's tile
+  bn_apply_rows<T>(x, residual, y, mask, sc_s - (size_t)blockIdx.x * width, sh_s - (size_t)blockIdx.x * width, C, cv, r0, r1, tyi, ty, relu);
+}
+
+// Backward twin: partial = [2][G][C] with S1 = sum dy*m and S2 = sum dy*m*xhat from the data-gradient epilogue of the convolution
+// that consumes this BatchNorm's output.  Every block reduces its channels' G rows, forms c1 = S1/R, c2 = S2/R, applies
+// dx = gamma*rstd*(dy*m - c1 - xhat*c2); the first row split also writes dgamma = S2, dbeta = S1.
+template <typename T>
+__global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_partials_kernel(const T* __restrict__ dy, const T* __restrict__ x, const unsigned char* __restrict__ y,
+                                                                          T* __restrict__ dx, T* __restrict__ dres, const float* __restrict__ partial, int G,
+                                                                          const float* __restrict__ save_mean, const float* __restrict__ save_rstd,
+                                                                          const float* __restrict__ gamma, float* __restrict__ dgamma,
+                                                                          float* __restrict__ dbeta, int R, int C, int cvb, int ty, int relu) {
+  extern __shared__ float bn_smem[];                 // [2][ty][cvb*8] reduction scratch, then [2][cvb*8] coefficients
+  const int tx = threadIdx.x % cvb, tyi = threadIdx.x / cvb;
+  const int cv = blockIdx.x * cvb + tx;
+  const bool live = cv * kVec < C;
+  float acc[2][kVec];
+#pragma unroll
+  for (int i = 0; i < kVec; ++i) { acc[0][i] = 0.f; acc[1][i] = 0.f; }
+  if (live) {
+    for (int g = tyi; g < G; g += ty) {
+      float a[kVec], b[kVec];
+      bn_load8<float>(partial + (size_t)g * C + cv * kVec, a);
+      bn_load8<float>(partial + ((size_t)G + g) * C + cv * kVec, b);
+#pragma unroll
+      for (int i = 0; i < kVec; ++i) { acc[0][i] += a[i]; acc[1][i] += b[i]; }
+    }
+  }
+  reduce_rows<2>(acc, bn_smem, tx, tyi, cvb, ty);
+  const int width = cvb * kVec;
+  float* c1_s = bn_smem + 2 * ty * width;            // coef layout expected by bn_bwd_apply_rows: c1 at [0, C), c2 at [C, 2C)
+  float* c2_s = c1_s + width;
+  if (tyi == 0 && live) {
+    const float inv_r = 1.f / (float)R;
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) {
+      const int ch = cv * kVec + i;
+      const float s1 = bn_smem[tx * kVec + i], s2 = bn_smem[ty * width + tx * kVec + i];
+      c1_s[tx * kVec + i] = s1 * inv_r;
+      c2_s[tx * kVec + i] = s2 * inv_r;
+      if (blockIdx.y == 0) { dgamma[ch] = s2; dbeta[ch] = s1; }
+    }
+  }
+  __syncthreads();
+  if (!live) return;
+  const int S = gridDim.y;
+  const int rows_per = (R + S - 1) / S;
+  const int r0 = blockIdx.y * rows_per, r1 = min(R, r0 + rows_per);
+  // bn_bwd_apply_rows reads coef[cv*8 + i] and coef[C + cv*8 + i]: rebase so that both land in this block's two smem rows
+  // (c2 row sits `width` floats after c1: a fake "C" of `width` would break the global indexing of the other operands, so the
+  // coefficients are passed through a two-pointer variant)
+  bn_bwd_apply_rows_coef<T>(dy, x, y, dx, dres, save_mean, save_rstd, gamma, c1_s + tx * kVec, c2_s + tx * kVec, C, cv, r0, r1, tyi, ty, relu);
 }
 
 void set_bn_pdl(int on) { g_bn_pdl = on; }
@@ -663,19 +749,39 @@ void launch_bn_forward_from_partials(const void* x, const void* residual, void* 
                                      const float* gamma, const float* beta, float* running_mean, float* running_var,
                                      long long* num_batches, float* save_mean, float* save_rstd, float* scale, float* shift,
                                      const float* partial, int groups, float eps, float momentum, bool relu, cudaStream_t s) {
+  (void)scale; (void)shift;                          // each block derives them for its own channels (see bn_apply_partials_kernel)
   if (C % kVec != 0) throw std::runtime_error("fused batch norm: channel count must be a multiple of 8");
   if (groups < 1) throw std::runtime_error("fused batch norm: empty partial statistics");
-  bn_finish_partials_kernel<<<(C + 31) / 32, 1024, 0, s>>>(partial, groups, C, R, gamma, beta, running_mean, running_var, num_batches,
-                                                         save_mean, save_rstd, scale, shift, eps, momentum);
-  B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
   const Tile t = pick_tile(R, C);
   const int r = relu ? 1 : 0;
+  const size_t smem = (size_t)(2 * t.ty + 2) * t.cvb * kVec * sizeof(float);
   if (dt == DType::BF16)
-    bn_apply_kernel<__nv_bfloat16><<<apply_grid(t, R), kBnThreads, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)residual,
-                                                                           (__nv_bfloat16*)y, mask, scale, shift, R, C, t.cvb, t.ty, r);
+    bn_apply_partials_kernel<__nv_bfloat16><<<apply_grid(t, R), kBnThreads, smem, s>>>(
+        (const __nv_bfloat16*)x, (const __nv_bfloat16*)residual, (__nv_bfloat16*)y, mask, partial, groups, gamma, beta, running_mean, running_var,
+        num_batches, save_mean, save_rstd, eps, momentum, R, C, t.cvb, t.ty, r);
   else
-    bn_apply_kernel<float><<<apply_grid(t, R), kBnThreads, 0, s>>>((const float*)x, (const float*)residual, (float*)y, mask, scale, shift, R, C,
-                                                                   t.cvb, t.ty, r);
+    bn_apply_partials_kernel<float><<<apply_grid(t, R), kBnThreads, smem, s>>>(
+        (const float*)x, (const float*)residual, (float*)y, mask, partial, groups, gamma, beta, running_mean, running_var, num_batches, save_mean,
+        save_rstd, eps, momentum, R, C, t.cvb, t.ty, r);
+  B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
+}
+
+void launch_bn_backward_from_partials(const void* dy, const void* x, const void* y, void* dx, void* dres, DType dt, int R, int C, const float* gamma,
+                                      const float* save_mean, const float* save_rstd, float* dgamma, float* dbeta, const float* partial, int groups,
+                                      bool relu, cudaStream_t s) {
+  if (C % kVec != 0) throw std::runtime_error("fused batch norm: channel count must be a multiple of 8");
+  if (groups < 1) throw std::runtime_error("fused batch norm: empty partial sums");
+  const Tile t = pick_tile(R, C);
+  const int r = relu ? 1 : 0;
+  const size_t smem = (size_t)(2 * t.ty + 2) * t.cvb * kVec * sizeof(float);
+  if (dt == DType::BF16)
+    bn_bwd_apply_partials_kernel<__nv_bfloat16><<<apply_grid(t, R), kBnThreads, smem, s>>>(
+        (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const unsigned char*)y, (__nv_bfloat16*)dx, (__nv_bfloat16*)dres, partial, groups, save_mean,
+        save_rstd, gamma, dgamma, dbeta, R, C, t.cvb, t.ty, r);
+  else
+    bn_bwd_apply_partials_kernel<float><<<apply_grid(t, R), kBnThreads, smem, s>>>(
+        (const float*)dy, (const float*)x, (const unsigned char*)y, (float*)dx, (float*)dres, partial, groups, save_mean, save_rstd, gamma, dgamma, dbeta,
+        R, C, t.cvb, t.ty, r);
   B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
 }
 

@@ -500,7 +500,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     return std::make_tuple(y, st);
   }, py::arg("x"), py::arg("w"), py::arg("stride") = 1, py::arg("pad") = 0, py::arg("mode") = -1, py::arg("block_n") = 0,
      py::arg("base_offset") = 0, py::arg("stats") = false, py::arg("debug") = py::none(), py::arg("kc") = 0);
-  m.def("conv_dgrad", [](at::Tensor dy, at::Tensor w, int stride, int pad, int mode, int block_n, int base_offset, int kc) {
+  // optional epilogue fusion: addend [N,C,H,W] is added to dx; (bn_x, bn_mask, bn_stats) make the epilogue also emit the partial
+  // sums of the BatchNorm backward that consumes dx (returned as the second tensor, [2, G, C]; empty otherwise)
+  m.def("conv_dgrad", [](at::Tensor dy, at::Tensor w, int stride, int pad, int mode, int block_n, int base_offset, int kc,
+                         c10::optional<at::Tensor> addend, c10::optional<at::Tensor> bn_x, c10::optional<at::Tensor> bn_mask,
+                         c10::optional<at::Tensor> bn_stats) {
     check_cuda(dy, "dy"); check_cuda(w, "w");
     TORCH_CHECK(dy.scalar_type() == at::kBFloat16 && w.scalar_type() == at::kBFloat16, "conv_dgrad: bf16 tensors");
     TORCH_CHECK(dy.dim() == 4 && dy.is_contiguous(at::MemoryFormat::ChannelsLast), "conv_dgrad: dy must be 4-D channels_last");
@@ -511,10 +515,39 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     const int N = (int)dy.size(0), K = (int)dy.size(1), H = (int)dy.size(2), W = (int)dy.size(3), C = (int)w.size(1);
     at::Tensor dx = at::empty({N, C, H, W}, dy.options().memory_format(at::MemoryFormat::ChannelsLast));
     ConvLaunchCfg cfg; cfg.mode = mode; cfg.block_n = block_n; cfg.set_base_offset = base_offset; cfg.kc = kc;
-    launch_conv_tap_gemm(dy.data_ptr(), w.data_ptr(), dx.data_ptr(), N, H, W, C, K, R, S, true, cfg, nullptr, cur_stream());
-    return dx;
+    ConvBwdFusion fuse;
+    bool any = false;
+    at::Tensor part;
+    float* pp = nullptr;
+    if (addend.has_value()) {
+      TORCH_CHECK(addend->sizes() == dx.sizes() && addend->scalar_type() == at::kBFloat16 && addend->is_contiguous(at::MemoryFormat::ChannelsLast),
+                  "conv_dgrad: addend must match dx (bf16, channels_last)");
+      fuse.addend = addend->data_ptr(); any = true;
+    }
+    if (bn_x.has_value()) {
+      TORCH_CHECK(bn_stats.has_value() && bn_stats->scalar_type() == at::kFloat && bn_stats->dim() == 2 && bn_stats->size(1) == C && bn_stats->size(0) >= 2,
+                  "conv_dgrad: bn_stats must be fp32 [>=2, C] (rows: mean, rstd)");
+      TORCH_CHECK(bn_x->sizes() == dx.sizes() && bn_x->scalar_type() == at::kBFloat16 && bn_x->is_contiguous(at::MemoryFormat::ChannelsLast),
+                  "conv_dgrad: bn_x must match dx (bf16, channels_last)");
+      fuse.bn_x = bn_x->data_ptr();
+      if (bn_mask.has_value()) {
+        TORCH_CHECK(bn_mask->scalar_type() == at::kByte && bn_mask->numel() == (int64_t)N * H * W * (C / 8), "conv_dgrad: bn_mask must be uint8 [N*H*W, C/8]");
+        fuse.bn_mask = bn_mask->data_ptr();
+      }
+      fuse.bn_mean = bn_stats->data_ptr<float>();
+      fuse.bn_rstd = bn_stats->data_ptr<float>() + C;
+      // the statistics workspace of the data gradient has one row per CTA of an n-tile over the Cin columns
+      const int groups = conv_stat_groups(N, H, W, K, C, R, S, cfg);
+      TORCH_CHECK(groups > 0, "conv_dgrad: no tile plan");
+      part = at::empty({2, groups, C}, dy.options().dtype(at::kFloat));
+      pp = part.data_ptr<float>();
+      any = true;
+    }
+    launch_conv_tap_gemm(dy.data_ptr(), w.data_ptr(), dx.data_ptr(), N, H, W, C, K, R, S, true, cfg, pp, cur_stream(), any ? &fuse : nullptr);
+    return std::make_tuple(dx, part);
   }, py::arg("dy"), py::arg("w"), py::arg("stride") = 1, py::arg("pad") = 0, py::arg("mode") = -1, py::arg("block_n") = 0,
-     py::arg("base_offset") = 0, py::arg("kc") = 0);
+     py::arg("base_offset") = 0, py::arg("kc") = 0, py::arg("addend") = py::none(), py::arg("bn_x") = py::none(),
+     py::arg("bn_mask") = py::none(), py::arg("bn_stats") = py::none());
   m.def("conv_wgrad", [](at::Tensor dy, at::Tensor x, int ksize, int stride, int pad, int split, int tile_m, int tile_n) {
     check_cuda(dy, "dy"); check_cuda(x, "x");
     TORCH_CHECK(dy.scalar_type() == at::kBFloat16 && x.scalar_type() == at::kBFloat16, "conv_wgrad: bf16 tensors");
@@ -602,6 +635,26 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
                                     num_batches.has_value() ? (long long*)num_batches->data_ptr<int64_t>() : nullptr, st, st + C, st + 2 * C,
                                     st + 3 * C, partial.data_ptr<float>(), (int)partial.size(1), (float)eps, (float)momentum, relu, cur_stream());
     return std::make_tuple(y, stats, mask);
+  });
+  m.def("bn_backward_partials", [](at::Tensor dy, at::Tensor x, c10::optional<at::Tensor> y, at::Tensor gamma, at::Tensor stats, bool relu,
+                                   bool need_dres, at::Tensor partial) {
+    check_cuda(dy, "dy"); check_cuda(partial, "partial");
+    c10::cuda::CUDAGuard guard(x.device());
+    const int C = (int)x.size(1);
+    const int R = (int)(x.numel() / C);
+    TORCH_CHECK(partial.scalar_type() == at::kFloat && partial.dim() == 3 && partial.size(0) == 2 && partial.size(2) == C && partial.is_contiguous(),
+                "bn_backward_partials: partial sums must be fp32 [2, groups, C]");
+    TORCH_CHECK(dy.is_contiguous(at::MemoryFormat::ChannelsLast) && dy.sizes() == x.sizes() && dy.dtype() == x.dtype(), "bn_backward_partials: dy must match x");
+    at::Tensor dx = at::empty_like(x);
+    at::Tensor dres = need_dres ? at::empty_like(x) : at::Tensor();
+    at::Tensor dparams = at::empty({2, C}, x.options().dtype(at::kFloat));   // rows: dgamma, dbeta
+    float* dp = dparams.data_ptr<float>();
+    const float* st = stats.data_ptr<float>();
+    TORCH_CHECK(!relu || (y.has_value() && y->scalar_type() == at::kByte), "bn_backward_partials: needs the ReLU bitmask written by bn_forward");
+    launch_bn_backward_from_partials(dy.data_ptr(), x.data_ptr(), relu ? y->data_ptr() : nullptr, dx.data_ptr(), need_dres ? dres.data_ptr() : nullptr,
+                                     dtype_of(x), R, C, gamma.data_ptr<float>(), st, st + C, dp, dp + C, partial.data_ptr<float>(), (int)partial.size(1),
+                                     relu, cur_stream());
+    return std::make_tuple(dx, dres, dparams);
   });
   m.def("bn_backward", [](at::Tensor dy, at::Tensor x, c10::optional<at::Tensor> y, at::Tensor gamma, at::Tensor stats, bool relu,
                           bool need_dres, at::Tensor partial, at::Tensor counters) {

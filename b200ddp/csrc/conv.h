@@ -36,8 +36,19 @@ struct ConvLaunchCfg {
 // Data gradient (dgrad = true): dx[N,H,W,Cin] = conv^T(dy[N,H,W,Cout], w[Cout,R,S,Cin]) - same kernel, mirrored taps, filter read MN-major.
 // `a` is x (or dy), `d` the output; R = S in {1, 3}.  col_stats (forward only, optional): [2][conv_stat_groups(...)][Cout] fp32 partial
 // column sums / sums of squares of the stored output (BatchNorm statistics from the epilogue).
+// Data-gradient epilogue fusion (optional): `addend` [N,H,W,Cin] is added to dx (the shortcut gradient of a residual block - no
+// separate add kernel); and if `bn_x` is given, dx is the output gradient of the BatchNorm(+ReLU) whose input was bn_x: the
+// epilogue then also writes per-CTA partial sums S1 = sum dx*m, S2 = sum dx*m*xhat into col_stats ([2][conv_stat_groups][Cin]),
+// which replaces that BatchNorm's backward reduction pass over dx and bn_x.
+struct ConvBwdFusion {
+  const void* addend = nullptr;
+  const void* bn_x = nullptr;
+  const void* bn_mask = nullptr;     // [N*H*W, Cin / 8] bit mask (ReLU) or nullptr
+  const float* bn_mean = nullptr;
+  const float* bn_rstd = nullptr;
+};
 void launch_conv_tap_gemm(const void* a, const void* w, void* d, int N, int H, int W, int Cin, int Cout, int R, int S, bool dgrad,
-                          const ConvLaunchCfg& cfg, float* col_stats, cudaStream_t stream);
+                          const ConvLaunchCfg& cfg, float* col_stats, cudaStream_t stream, const ConvBwdFusion* fuse = nullptr);
 
 
 // rows G of the column-statistics workspace [2][G][Cout] the forward launch with this configuration will write

@@ -42,6 +42,8 @@ constexpr int kMaxRing = 12;
 constexpr int kSlabBytes = 128 * 128;          // one dense staging tile: 128 rows x 64 bf16
 constexpr int kStagingBytes = 2 * kSlabBytes;
 constexpr int kBarrierBytes = 1024;
+constexpr int kTrStride = 36;                       // floats per row of the per-warp 32 x 32 transpose scratch (conflict-free v4 stores / column loads)
+constexpr int kStatsScratchBytes = 4 * 32 * kTrStride * 4;   // epilogue statistics scratch: one 32 x 36 fp32 tile per epilogue warp
 
 struct TapGemmParams {
   int M_total, Kc, Nc;      // output pixels, reduction channels per tap, output channels
@@ -58,7 +60,12 @@ struct TapGemmParams {
   uint32_t a_tx_bytes;
   int set_base_offset;
   int b_tap_stride;         // column distance between taps in the filter matrix (Cin of the filter tensor)
-  float* col_stats;         // [2][num_m_tiles * 4][Nc] or nullptr
+  float* col_stats;         // [2][G][Nc] or nullptr (EPI 1: sum / sum of squares of the output; EPI 2: S1 / S2 of the BatchNorm backward)
+  const __nv_bfloat16* addend;   // EPI 2: [M_total, Nc] added to the output (shortcut gradient) or nullptr
+  const __nv_bfloat16* bn_x;     // EPI 2: [M_total, Nc] input of the BatchNorm whose backward consumes the output, or nullptr
+  const uint8_t* bn_mask;        // EPI 2: [M_total, Nc / 8] ReLU bit mask of that BatchNorm's output, or nullptr (no ReLU)
+  const float* bn_mean;          // EPI 2: [Nc]
+  const float* bn_rstd;          // EPI 2: [Nc]
   long long* dbg;           // optional [16] cycle counters of CTA 0's roles (diagnostics)
 };
 
@@ -88,18 +95,19 @@ __device__ __forceinline__ bool acc_row_to_dense(const TapGemmParams& p, int i, 
   return i < p.dense_rows;
 }
 
-__device__ __forceinline__ float warp_column_sum32(float* t, int lane) {
+// Column sums of a 32-row x 32-column block held one row per lane: the block goes through a per-warp shared-memory tile
+// (row stride 36 floats: the eight 16-byte stores of a row and the 32 column reads are bank-conflict free) and lane l adds up
+// column l.  ~1.7x fewer instructions than a shuffle butterfly, which made small-K layers epilogue-bound.
+__device__ __forceinline__ float warp_column_sum32(const float* v, float* tr, int lane) {
 #pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    const bool upper = (lane & off) != 0;
+  for (int q = 0; q < 8; ++q)
+    *reinterpret_cast<float4*>(tr + lane * kTrStride + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  __syncwarp();
+  float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < off; ++i) {
-      const float keep = upper ? t[i + off] : t[i];
-      const float send = upper ? t[i] : t[i + off];
-      t[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-  return t[0];
+  for (int r = 0; r < 32; ++r) s += tr[r * kTrStride + lane];
+  __syncwarp();
+  return s;
 }
 
 // exactly one lane of a converged warp; code guarded by it is known single-threaded to the compiler, which keeps
@@ -111,7 +119,9 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-template <int BLOCK_N, bool B_MN, bool STATS>
+// EPI: 0 plain store; 1 forward + column statistics of the output (BatchNorm forward); 2 data gradient + optional addend
+// (shortcut gradient) + optional partial sums of the BatchNorm backward that consumes this gradient
+template <int BLOCK_N, bool B_MN, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tap_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                      const __grid_constant__ CUtensorMap map_d, const TapGemmParams p) {
@@ -124,7 +134,8 @@ conv_tap_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   uint8_t* s_ring = smem;
   uint8_t* b_ring = s_ring + p.s_stages * p.s_stage_bytes;
   uint8_t* staging = b_ring + p.b_stages * p.b_slot_bytes;
-  uint64_t* s_full = reinterpret_cast<uint64_t*>(staging + kStagingBytes);
+  [[maybe_unused]] float* stats_scratch = reinterpret_cast<float*>(staging + kStagingBytes);
+  uint64_t* s_full = reinterpret_cast<uint64_t*>(staging + kStagingBytes + (EPI != 0 ? kStatsScratchBytes : 0));
   uint64_t* s_empty = s_full + kMaxRing;
   uint64_t* b_full = s_empty + kMaxRing;
   uint64_t* b_empty = b_full + kMaxRing;
@@ -140,9 +151,9 @@ conv_tap_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   const int chunks_per_tile = cblocks * taps;              // flat / patch: 64-deep k chunks of one tile
 
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b); tma_prefetch_desc(&map_d); }
-  if (warp == 1 && lane == 0) {
-    for (int i = 0; i < kMaxRing; ++i) { mbar_init(&s_full[i], p.mode == 2 ? 1 : 2); mbar_init(&s_empty[i], 1); mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < kAccumStages; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+  if (warp == 1) {                                     // one lane per ring slot: the ~50 barrier inits are off the serial path
+    if (lane < kMaxRing) { mbar_init(&s_full[lane], p.mode == 2 ? 1 : 2); mbar_init(&s_empty[lane], 1); mbar_init(&b_full[lane], 1); mbar_init(&b_empty[lane], 1); }
+    if (lane >= 16 && lane < 16 + kAccumStages) { mbar_init(&tmem_full[lane - 16], 1); mbar_init(&tmem_empty[lane - 16], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -341,6 +352,8 @@ conv_tap_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     // STATS: the grid is a multiple of num_n_tiles, so every tile of this CTA has the same n-tile; after the butterfly a lane
     // owns column `lane` of each 32-column chunk and keeps its running sum / sum of squares in registers across tiles
     [[maybe_unused]] float st_s[BLOCK_N / 32], st_q[BLOCK_N / 32];
+    constexpr bool STATS = (EPI != 0);
+    [[maybe_unused]] float* tr = stats_scratch + ew * (32 * kTrStride);
     if constexpr (STATS) {
 #pragma unroll
       for (int i = 0; i < BLOCK_N / 32; ++i) { st_s[i] = 0.f; st_q[i] = 0.f; }
@@ -368,7 +381,7 @@ conv_tap_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           uint32_t rr[32];
           tmem_ld32(taddr + (uint32_t)(c + 32 * half), rr);
           tmem_ld_wait();
-          if constexpr (STATS) {
+          if constexpr (EPI == 1) {
             float sv[32], qv[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
@@ -376,12 +389,68 @@ conv_tap_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
               sv[i] = valid ? v : 0.f;
               qv[i] = sv[i] * sv[i];
             }
-            const float cs = warp_column_sum32(sv, lane);
-            const float cq = warp_column_sum32(qv, lane);
+            const float cs = warp_column_sum32(sv, tr, lane);
+            const float cq = warp_column_sum32(qv, tr, lane);
             const int ci = (c >> 5) + half;                 // 32-column chunk index inside the tile (compile-time after unrolling)
 #pragma unroll
             for (int i = 0; i < BLOCK_N / 32; ++i)
               if (i == ci) { st_s[i] += cs; st_q[i] += cq; }
+          }
+          if constexpr (EPI == 2) {
+            // data-gradient epilogue: (+ shortcut gradient) -> round to bf16 as stored -> partial sums of the BatchNorm backward that
+            // consumes this tensor: S1 = sum dy*m, S2 = sum dy*m*xhat  (m = ReLU mask of that BatchNorm's output, xhat from its input)
+            const int col0 = n0 + c + 32 * half;
+            const size_t grow = (size_t)(row0 + dense);
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[i]);
+            if (p.addend != nullptr && valid) {
+              const uint4* ap = reinterpret_cast<const uint4*>(p.addend + grow * p.Nc + col0);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint4 raw = __ldg(ap + q);
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(h[j]); v[8 * q + 2 * j] += f.x; v[8 * q + 2 * j + 1] += f.y; }
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { v[i] = __bfloat162float(__float2bfloat16_rn(v[i])); rr[i] = __float_as_uint(v[i]); }
+            if (p.bn_x != nullptr) {
+              float sv[32], qv[32];
+              uint32_t mk = 0xffffffffu;
+              float xv[32];
+              if (valid) {
+                const uint4* xp = reinterpret_cast<const uint4*>(p.bn_x + grow * p.Nc + col0);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const uint4 raw = __ldg(xp + q);
+                  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(h[j]); xv[8 * q + 2 * j] = f.x; xv[8 * q + 2 * j + 1] = f.y; }
+                }
+                if (p.bn_mask != nullptr) mk = __ldg(reinterpret_cast<const uint32_t*>(p.bn_mask + grow * (size_t)(p.Nc >> 3) + (col0 >> 3)));
+              } else {
+                mk = 0u;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) xv[i] = 0.f;
+              }
+              const float my_mean = (col0 + lane < p.Nc) ? __ldg(p.bn_mean + col0 + lane) : 0.f;
+              const float my_rstd = (col0 + lane < p.Nc) ? __ldg(p.bn_rstd + col0 + lane) : 0.f;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float mean_i = __shfl_sync(0xffffffffu, my_mean, i), rstd_i = __shfl_sync(0xffffffffu, my_rstd, i);
+                const float dyp = ((mk >> i) & 1u) ? v[i] : 0.f;
+                sv[i] = dyp;
+                qv[i] = dyp * (xv[i] - mean_i) * rstd_i;
+              }
+              const float cs = warp_column_sum32(sv, tr, lane);
+              const float cq = warp_column_sum32(qv, tr, lane);
+              const int ci = (c >> 5) + half;
+#pragma unroll
+              for (int i = 0; i < BLOCK_N / 32; ++i)
+                if (i == ci) { st_s[i] += cs; st_q[i] += cq; }
+            }
           }
           if (valid) {
 #pragma unroll
@@ -409,14 +478,27 @@ conv_tap_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       B200_T1(d_ep)
     }
     if (dbg) { p.dbg[8] = d_we; p.dbg[9] = d_ep; }
-    if constexpr (STATS) {
-      // one row of the workspace per (CTA of this n-tile, epilogue warp): [2][G = gridDim / num_n_tiles * 4][Nc]
-      const int nt = blockIdx.x % p.num_n_tiles;
-      const size_t g = (size_t)(blockIdx.x / p.num_n_tiles) * 4 + ew, G = (size_t)(gridDim.x / p.num_n_tiles) * 4;
+    if (STATS && p.col_stats != nullptr) {
+      // the four epilogue warps' sums are combined through shared memory (fixed order), then ONE row of the workspace per CTA:
+      // [2][G = gridDim / num_n_tiles][Nc], row = blockIdx / num_n_tiles, columns of this CTA's n-tile
+      float* comb = stats_scratch;                       // [4][2][BLOCK_N]
+      epi_bar_sync();                                    // everyone is done with the transpose scratch
 #pragma unroll
       for (int i = 0; i < BLOCK_N / 32; ++i) {
-        const int col = nt * BLOCK_N + 32 * i + lane;
-        if (col < p.Nc) { p.col_stats[g * p.Nc + col] = st_s[i]; p.col_stats[(G + g) * p.Nc + col] = st_q[i]; }
+        comb[(ew * 2 + 0) * BLOCK_N + 32 * i + lane] = st_s[i];
+        comb[(ew * 2 + 1) * BLOCK_N + 32 * i + lane] = st_q[i];
+      }
+      epi_bar_sync();
+      const int nt = blockIdx.x % p.num_n_tiles;
+      const size_t g = (size_t)(blockIdx.x / p.num_n_tiles), G = (size_t)(gridDim.x / p.num_n_tiles);
+      for (int j = ew * 32 + lane; j < 2 * BLOCK_N; j += 128) {
+        const int which = j / BLOCK_N, cc = j - which * BLOCK_N;
+        const int col = nt * BLOCK_N + cc;
+        if (col < p.Nc) {
+          const float v = ((comb[(0 * 2 + which) * BLOCK_N + cc] + comb[(1 * 2 + which) * BLOCK_N + cc]) + comb[(2 * 2 + which) * BLOCK_N + cc]) +
+                          comb[(3 * 2 + which) * BLOCK_N + cc];
+          p.col_stats[((size_t)which * G + g) * p.Nc + col] = v;
+        }
       }
     }
     if (t0) bulk_wait_all();                         // staging memory must outlive the last store
@@ -559,16 +641,16 @@ int conv_stat_groups(int N, int H, int W, int Cin, int Cout, int R, int S, const
   if (!conv_tile_plan(N, H, W, R, S, mode, &pl)) return 0;
   const int bn = conv_pick_block_n(Cout, pl.num_m_tiles, cfg.block_n);
   const int nn = ceil_div(Cout, bn);
-  return conv_grid_size(pl.num_m_tiles, nn, true) / nn * 4;
+  return conv_grid_size(pl.num_m_tiles, nn, true) / nn;
 }
 
 namespace {
 
-template <int BLOCK_N, bool B_MN, bool STATS>
+template <int BLOCK_N, bool B_MN, int EPI>
 void launch_variant(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md, TapGemmParams p, int want_kc, cudaStream_t stream) {
   constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
   // All shared memory that is not the epilogue staging is ring depth.
-  const int budget = 227 * 1024 - kStagingBytes - kBarrierBytes - 1024;
+  const int budget = 227 * 1024 - kStagingBytes - kBarrierBytes - 1024 - (EPI != 0 ? kStatsScratchBytes : 0);
   const int taps = p.R * p.S;
   if (p.mode != 2) {
     // ring S stage = KC x (activation chunk + filter chunk): one barrier wait + one tcgen05.commit per KC * 4 MMAs
@@ -597,14 +679,14 @@ void launch_variant(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensor
     if (b_st < 2) throw std::runtime_error("conv: shared memory budget exceeded");
     p.s_stages = s_st; p.b_stages = b_st;
   }
-  const int smem = p.s_stages * p.s_stage_bytes + p.b_stages * p.b_slot_bytes + kStagingBytes + kBarrierBytes + 1024;
-  auto kernel = conv_tap_gemm_kernel<BLOCK_N, B_MN, STATS>;
+  const int smem = p.s_stages * p.s_stage_bytes + p.b_stages * p.b_slot_bytes + kStagingBytes + kBarrierBytes + 1024 + (EPI != 0 ? kStatsScratchBytes : 0);
+  auto kernel = conv_tap_gemm_kernel<BLOCK_N, B_MN, EPI>;
   static bool configured = false;
   if (!configured) {
     B200_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  const int grid = conv_grid_size(p.num_m_tiles, p.num_n_tiles, STATS);
+  const int grid = conv_grid_size(p.num_m_tiles, p.num_n_tiles, EPI != 0);
   kernel<<<grid, kThreads, smem, stream>>>(ma, mb, md, p);
   B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);
 }
@@ -612,11 +694,13 @@ void launch_variant(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensor
 }  // namespace
 
 void launch_conv_tap_gemm(const void* a, const void* w, void* d, int N, int H, int W, int Cin, int Cout, int R, int S, bool dgrad,
-                          const ConvLaunchCfg& cfg, float* col_stats, cudaStream_t stream) {
+                          const ConvLaunchCfg& cfg, float* col_stats, cudaStream_t stream, const ConvBwdFusion* fuse) {
   const int Kc = dgrad ? Cout : Cin, Nc = dgrad ? Cin : Cout;
   if (Kc % BLOCK_K != 0 || Nc % 64 != 0) throw std::runtime_error("conv: channel counts must be multiples of 64");
   if (R != S || (R != 1 && R != 3)) throw std::runtime_error("conv: 1x1 or 3x3 filters");
-  if (dgrad && col_stats != nullptr) throw std::runtime_error("conv: column statistics ride on the forward pass only");
+  if (dgrad && fuse == nullptr && col_stats != nullptr) throw std::runtime_error("conv: column statistics ride on the forward pass only");
+  if (fuse != nullptr && !dgrad) throw std::runtime_error("conv: the BatchNorm-backward fusion rides on the data gradient");
+  if (fuse != nullptr && fuse->bn_x != nullptr && col_stats == nullptr) throw std::runtime_error("conv: fused BatchNorm backward needs the partial-sum workspace");
   ConvTilePlan pl;
   int mode = cfg.mode;
   // 3x3 tilings, measured: the halo tiling wins when a tile's filter taps are small (64 reduction channels: layer1), the
@@ -638,6 +722,11 @@ void launch_conv_tap_gemm(const void* a, const void* w, void* d, int N, int H, i
   p.set_base_offset = cfg.set_base_offset;
   p.b_tap_stride = Cin;
   p.col_stats = col_stats;
+  p.addend = fuse ? reinterpret_cast<const __nv_bfloat16*>(fuse->addend) : nullptr;
+  p.bn_x = fuse ? reinterpret_cast<const __nv_bfloat16*>(fuse->bn_x) : nullptr;
+  p.bn_mask = fuse ? reinterpret_cast<const uint8_t*>(fuse->bn_mask) : nullptr;
+  p.bn_mean = fuse ? fuse->bn_mean : nullptr;
+  p.bn_rstd = fuse ? fuse->bn_rstd : nullptr;
   p.dbg = reinterpret_cast<long long*>(cfg.debug_counters);
   const int block_n = conv_pick_block_n(Nc, pl.num_m_tiles, cfg.block_n);
   if (block_n != 64 && block_n != 128 && block_n != 256) throw std::runtime_error("conv: block_n must be 64, 128 or 256");
@@ -674,9 +763,10 @@ void launch_conv_tap_gemm(const void* a, const void* w, void* d, int N, int H, i
   }
 #define B200_CONV_DISPATCH(BN)                                                                         \
   if (block_n == BN) {                                                                                 \
-    if (dgrad) launch_variant<BN, true, false>(ma, mb, md, p, cfg.kc, stream);                         \
-    else if (col_stats != nullptr) launch_variant<BN, false, true>(ma, mb, md, p, cfg.kc, stream);     \
-    else launch_variant<BN, false, false>(ma, mb, md, p, cfg.kc, stream);                              \
+    if (dgrad && fuse != nullptr) launch_variant<BN, true, 2>(ma, mb, md, p, cfg.kc, stream);          \
+    else if (dgrad) launch_variant<BN, true, 0>(ma, mb, md, p, cfg.kc, stream);                        \
+    else if (col_stats != nullptr) launch_variant<BN, false, 1>(ma, mb, md, p, cfg.kc, stream);        \
+    else launch_variant<BN, false, 0>(ma, mb, md, p, cfg.kc, stream);                                  \
     return;                                                                                            \
   }
   B200_CONV_DISPATCH(64)

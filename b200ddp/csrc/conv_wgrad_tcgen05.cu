@@ -90,9 +90,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
   const int a_chunks = p.MB * 2, b_chunks = p.tile_n / 64;
 
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_dy); tma_prefetch_desc(&map_x); }
-  if (warp == 1 && lane == 0) {
-    for (int i = 0; i < kMaxRing; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    mbar_init(acc_full, 1);
+  if (warp == 1) {
+    if (lane < kMaxRing) { mbar_init(&a_full[lane], 1); mbar_init(&a_empty[lane], 1); mbar_init(&b_full[lane], 1); mbar_init(&b_empty[lane], 1); }
+    if (lane == 16) mbar_init(acc_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {

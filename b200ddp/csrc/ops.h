@@ -82,6 +82,11 @@ void launch_bn_forward_from_partials(const void* x, const void* residual, void* 
                                      const float* gamma, const float* beta, float* running_mean, float* running_var,
                                      long long* num_batches, float* save_mean, float* save_rstd, float* scale, float* shift,
                                      const float* partial, int groups, float eps, float momentum, bool relu, cudaStream_t s);
+// Backward with S1 / S2 partial sums ([2][groups][C]) from the data-gradient epilogue of the consuming convolution: one launch
+// (reduce the partials per block, apply), no pass over dy and x for the reduction.
+void launch_bn_backward_from_partials(const void* dy, const void* x, const void* relu_mask, void* dx, void* dres, DType dt, int R, int C, const float* gamma,
+                                      const float* save_mean, const float* save_rstd, float* dgamma, float* dbeta, const float* partial, int groups,
+                                      bool relu, cudaStream_t s);
 void launch_bn_backward(const void* dy, const void* x, const void* relu_mask, void* dx, void* dres, DType dt, int R, int C, const float* gamma,
                         const float* save_mean, const float* save_rstd, float* dgamma, float* dbeta, float* coef, float* partial,
                         unsigned int* counters, bool relu, cudaStream_t s);

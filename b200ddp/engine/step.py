@@ -29,14 +29,20 @@ class TrainStep:
         self.accumulation = max(1, int(accumulation))
         self.input_transform = input_transform
         self.target_transform = target_transform
-        self.use_graph = bool(use_graph) and self.device.type == "cuda" and self.accumulation == 1
+        self.use_graph = bool(use_graph) and self.device.type == "cuda"
         self.graph_warmup = graph_warmup
         # static loss scaling (the reference's --loss_scale, ddp.py:179/307): the loss is multiplied before backward and the
         # optimizer divides the gradients again inside the fused kernel (grad_scale); bf16 needs none, so the default is 1
         self.loss_scale = float(loss_scale) if loss_scale and loss_scale > 0 else 1.0
         if self.loss_scale != 1.0 and hasattr(optimizer, "grad_scale"):
             optimizer.grad_scale = 1.0 / self.loss_scale
-        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        # accumulation == 1: one graph ("single").  accumulation > 1: a window of micro-steps replays "first" (gradients are
+        # written into static buffers), "middle" x (accumulation - 2) (accumulate in place, no communication) and "last"
+        # (accumulate, DDP reduction, clip + SGD) - three graphs over the same static gradient buffers and one memory pool.
+        self.graph: Optional[torch.cuda.CUDAGraph] = None          # "single" or "last": the graph that holds the optimizer
+        self._graphs = {}
+        self._window_pos = 0
+        self._rebuilt = False
         self._static_x = self._static_y = self._static_loss = None
         self._graph_shapes = None
         self._eager_iters = 0
@@ -84,7 +90,6 @@ class TrainStep:
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         self.optimizer.zero_grad(set_to_none=True)
-        g = torch.cuda.CUDAGraph()
         counter = None
         try:
             from .. import _ext
@@ -92,16 +97,34 @@ class TrainStep:
         except Exception:
             pass
         before = counter() if counter else 0
+        kinds = ["single"] if self.accumulation == 1 else (["first"] + (["middle"] if self.accumulation > 2 else []) + ["last"])
+        pool = None
+        self._static_loss = torch.zeros((), dtype=torch.float32, device=self.device)
         with torch.cuda.stream(side):
-            with torch.cuda.graph(g, stream=side):
-                loss = self._fwd_bwd(self._static_x, self._static_y, True)
-                self._apply_optimizer()
-                self._static_loss = loss.float() if loss.dtype != torch.float32 else loss
-                self.loss_sum.add_(self._static_loss)
+            for kind in kinds:
+                g = torch.cuda.CUDAGraph()
+                boundary = kind in ("single", "last")
+                # "first" is captured with .grad == None, so autograd leaves freshly written gradients in static (pool)
+                # buffers; the later captures find those tensors in .grad and accumulate into them in place
+                with torch.cuda.graph(g, stream=side, pool=pool):
+                    loss = self._fwd_bwd(self._static_x, self._static_y, boundary)
+                    if boundary:
+                        self._apply_optimizer()
+                    self._static_loss.copy_(loss.float() if loss.dtype != torch.float32 else loss)
+                    self.loss_sum.add_(self._static_loss)
+                pool = g.pool()
+                self._graphs[kind] = g
         torch.cuda.current_stream(self.device).wait_stream(side)
-        self.graph = g
-        # native (b200ddp extension) kernel launches recorded in the graph = executed on every replay
+        self.graph = self._graphs[kinds[-1]]
+        # native (b200ddp extension) kernel launches recorded while capturing (one of each graph kind)
         self.captured_native_launches = (counter() - before) if counter else 0
+
+    def _replay_kind(self) -> str:
+        if self.accumulation == 1:
+            return "single"
+        if self._window_pos == 0:
+            return "first"
+        return "last" if self._window_pos == self.accumulation - 1 else "middle"
 
     def _graph_ok(self, x, y) -> bool:
         return self._graph_shapes == (tuple(x.shape), x.dtype, tuple(y.shape), y.dtype)
@@ -116,7 +139,7 @@ class TrainStep:
             y = self.target_transform(y)
         self.micro_steps += 1
         if self.use_graph:
-            if self.graph is None and self._eager_iters >= self.graph_warmup:
+            if self.graph is None and self._eager_iters >= self.graph_warmup * self.accumulation and self._window_pos == 0:
                 self._capture(x, y)
                 # the capture itself does not execute; fall through to replay for this batch
             if self.graph is not None and self._graph_ok(x, y):
@@ -124,12 +147,16 @@ class TrainStep:
                     self._static_x.copy_(x, non_blocking=True)
                 if y.data_ptr() != self._static_y.data_ptr():
                     self._static_y.copy_(y, non_blocking=True)
-                self.graph.replay()
+                kind = self._replay_kind()
+                if (kind in ("single", "last")) != bool(boundary):
+                    raise RuntimeError("TrainStep: `boundary` must be True exactly on every accumulation-th micro-step under --cuda_graph")
+                self._graphs[kind].replay()
+                self._window_pos = 0 if boundary else self._window_pos + 1
                 return self._static_loss
-        # eager path (CPU, accumulation, graph warm-up, odd-shaped tail batch)
-        if self.graph is not None:
+        # eager path (CPU, graph warm-up, odd-shaped tail batch)
+        if self.graph is not None and self._window_pos == 0:
             # grads are graph-owned static buffers: leave them in place, the eager pass accumulates into
-            # zeroed copies instead
+            # fresh ones instead
             for p in self.model.parameters():
                 if p.grad is not None:
                     p.grad = None
@@ -138,6 +165,14 @@ class TrainStep:
         if boundary:
             self._apply_optimizer()
             self.optimizer.zero_grad(set_to_none=True)
+            if not self._rebuilt:
+                # what stock DDP does once after the first iteration when find_unused_parameters=False: re-plan
+                # the buckets by the gradient-ready order just observed - before any graph is captured
+                self._rebuilt = True
+                if getattr(self.model, "world_size", 1) > 1 and hasattr(self.model, "rebuild_buckets") \
+                        and not getattr(self.model, "find_unused_parameters", True):
+                    self.model.rebuild_buckets()
+        self._window_pos = 0 if boundary else self._window_pos + 1
         self._eager_iters += 1
         return loss
 

@@ -2,7 +2,7 @@
 Every linear is a ``b200ddp.ops.Linear`` (tcgen05 GEMM with bias / bias+GELU epilogues), every
 LayerNorm the hand-written kernel, the loss the fused cross-entropy; attention uses torch's SDPA
 (library flash attention - not a named hot op).  109.5 M encoder parameters as in SURVEY §2.4-K4
-(199 tensors) when built with ``with_mlm_head=False``."""
+(199 tensors in the stock naming; 151 here because Q / K / V are one stored parameter) when built with ``with_mlm_head=False``."""
 from __future__ import annotations
 
 from dataclasses import dataclass
@@ -55,9 +55,10 @@ class BertLayer(nn.Module):
     def __init__(self, c: BertConfig):
         super().__init__()
         self.heads = c.heads
-        self.query = Linear(c.hidden, c.hidden)
-        self.key = Linear(c.hidden, c.hidden)
-        self.value = Linear(c.hidden, c.hidden)
+        # Q, K and V projections are ONE stored [3*hidden, hidden] parameter (rows: query, key, value): forward, dgrad and
+        # wgrad are one tcgen05 launch each and nothing is concatenated per step.  ``load_hf_state_dict`` fuses the stock
+        # model's three tensors; ``split_qkv_state_dict`` gives them back.
+        self.qkv = Linear(c.hidden, 3 * c.hidden)
         self.attn_out = Linear(c.hidden, c.hidden)
         self.attn_norm = LayerNorm(c.hidden, eps=c.eps)
         self.ffn_in = Linear(c.hidden, c.intermediate, activation="gelu")
@@ -72,13 +73,7 @@ class BertLayer(nn.Module):
         def split(t):
             return t.view(B, S, self.heads, hd).transpose(1, 2)
 
-        # one [hidden -> 3*hidden] GEMM for Q, K and V: the three parameter tensors stay separate (same names, shapes and
-        # bucket layout as the stock model) and are concatenated on the fly (3.5 MB copy) so forward, dgrad and wgrad are
-        # one tcgen05 launch each instead of three
-        from ..ops import linear as _linear
-        w = torch.cat([self.query.weight, self.key.weight, self.value.weight], dim=0)
-        b = torch.cat([self.query.bias, self.key.bias, self.value.bias], dim=0)
-        qkv = _linear(x, w, b)
+        qkv = self.qkv(x)
         q, k, v = (split(t) for t in qkv.split(H, dim=-1))
         a = F.scaled_dot_product_attention(q, k, v, attn_mask=attn_mask)
         a = a.transpose(1, 2).reshape(B, S, H)
@@ -128,8 +123,7 @@ class BertForMaskedLM(nn.Module):
 
 
     # ---- interchange with the stock (Hugging Face) parameter naming ---------------------------------------
-    _LAYER_MAP = (("attention.self.query", "query"), ("attention.self.key", "key"), ("attention.self.value", "value"),
-                  ("attention.output.dense", "attn_out"), ("attention.output.LayerNorm", "attn_norm"),
+    _LAYER_MAP = (("attention.output.dense", "attn_out"), ("attention.output.LayerNorm", "attn_norm"),
                   ("intermediate.dense", "ffn_in"), ("output.dense", "ffn_out"), ("output.LayerNorm", "ffn_norm"))
 
     def load_hf_state_dict(self, hf: dict) -> None:
@@ -157,10 +151,25 @@ class BertForMaskedLM(nn.Module):
             for i in range(c.layers):
                 for src, dst in self._LAYER_MAP:
                     put(f"bert.encoder.{i}.{dst}.{wb}", f"bert.encoder.layer.{i}.{src}.{wb}")
+                # the stock model's separate query / key / value tensors become the rows of the fused projection
+                out[f"bert.encoder.{i}.qkv.{wb}"] = torch.cat(
+                    [hf[f"bert.encoder.layer.{i}.attention.self.{n}.{wb}"] for n in ("query", "key", "value")], dim=0).to(own[f"bert.encoder.{i}.qkv.{wb}"].dtype)
             put(f"transform.{wb}", f"cls.predictions.transform.dense.{wb}")
             put(f"transform_norm.{wb}", f"cls.predictions.transform.LayerNorm.{wb}")
         put("decoder_bias", "cls.predictions.bias")
         self.load_state_dict(out, strict=True)
+
+
+def split_qkv_state_dict(state: dict) -> dict:
+    """State dict with every fused ``qkv`` projection split back into ``query`` / ``key`` / ``value`` entries (the stock naming)."""
+    out = {}
+    for k, v in state.items():
+        if ".qkv." in k:
+            for n, part in zip(("query", "key", "value"), v.chunk(3, dim=0)):
+                out[k.replace(".qkv.", f".{n}.")] = part.clone()
+        else:
+            out[k] = v
+    return out
 
 
 def bert_base(with_mlm_head: bool = True) -> nn.Module:

@@ -4,12 +4,14 @@ run on this package's kernels; parameter order / shapes match torchvision's - bu
 therefore hold.  The 7x7 stem and the six stride-2 convolutions stay on the library."""
 from __future__ import annotations
 
+import os
 from typing import List
 
 import torch
 import torch.nn as nn
 
 from ..ops import Conv3x3, FusedBatchNormAct2d, Linear, MaxPool3x3s2, PointwiseConv2d
+from ..ops.bottleneck import bottleneck_forward, bottleneck_native_ok
 
 
 class Bottleneck(nn.Module):
@@ -28,6 +30,8 @@ class Bottleneck(nn.Module):
         self.downsample = downsample
 
     def forward(self, x):
+        if os.environ.get("B200DDP_BLOCK_FUSE", "0") == "1" and bottleneck_native_ok(self, x):
+            return bottleneck_forward(self, x)             # one autograd node, hand-written backward (ops/bottleneck.py)
         if self.downsample is None:
             identity = x
         else:

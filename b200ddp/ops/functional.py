@@ -133,15 +133,38 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
 # ------------------------------------------------------------------------------------------------
 # Convolutions on tcgen05 (csrc/conv_tcgen05.cu, csrc/conv_wgrad_tcgen05.cu)
 # ------------------------------------------------------------------------------------------------
-def _wgrad_native(cin: int, cout: int, k: int, pixels: int) -> bool:
-    """Which weight-gradient kernel runs: ours where it is at least level with the library per layer
-    (bench/conv_layers.py, profiles/conv_layers.md), the library's otherwise.  B200DDP_CONV_WGRAD=native|lib overrides."""
-    mode = os.environ.get("B200DDP_CONV_WGRAD", "auto")
+def _conv_policy() -> str:
+    """B200DDP_CONV: ``auto`` (default) = the hand-written tcgen05 kernels for the layer shapes where they beat the library
+    per layer (``profiles/conv_layers.md``), the library elsewhere; ``native`` = the tcgen05 kernels wherever they apply
+    (every stride-1 1x1 / 3x3 convolution: forward, data gradient, BatchNorm-statistics epilogue); ``lib`` = library only."""
+    return os.environ.get("B200DDP_CONV", "auto")
+
+
+def _fprop_native(cin: int, cout: int, k: int, pixels: int) -> bool:
+    mode = _conv_policy()
     if mode == "native":
         return True
     if mode == "lib":
         return False
-    return k == 1 and pixels >= 25088 and not (cin == 64 and cout == 64)
+    # measured wins (bench/conv_layers.py, batch 32): the memory-bound 64 -> 256 expansion of layer1 (14.2 us vs 18.2 us)
+    return k == 1 and cin == 64 and cout >= 256 and pixels >= 50176
+
+
+def _dgrad_native(cin: int, cout: int, k: int, pixels: int) -> bool:
+    """Data gradient: the tcgen05 kernel under ``native``; under ``auto`` no layer shape beats the library yet."""
+    return _conv_policy() == "native"
+
+
+def _wgrad_native(cin: int, cout: int, k: int, pixels: int) -> bool:
+    """Which weight-gradient kernel runs (B200DDP_CONV_WGRAD=native|lib|auto overrides; default follows B200DDP_CONV)."""
+    mode = os.environ.get("B200DDP_CONV_WGRAD", "auto")
+    if mode == "native":
+        return True
+    if mode == "lib" or _conv_policy() == "lib":
+        return False
+    if _conv_policy() == "native":
+        return k == 1 and pixels >= 25088 and not (cin == 64 and cout == 64)
+    return False
 
 
 def conv_tc_supported(x: torch.Tensor, weight: torch.Tensor, stride: int, padding: int) -> bool:
@@ -149,8 +172,15 @@ def conv_tc_supported(x: torch.Tensor, weight: torch.Tensor, stride: int, paddin
     k = weight.shape[2]
     return (x.is_cuda and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and x.dim() == 4 and stride == 1
             and weight.shape[2] == weight.shape[3] and k in (1, 3) and padding == (k - 1) // 2
-            and x.shape[1] % 64 == 0 and weight.shape[0] % 64 == 0 and x.shape[3] + 2 <= 256
-            and os.environ.get("B200DDP_CONV", "native") != "lib")
+            and x.shape[1] % 64 == 0 and weight.shape[0] % 64 == 0 and x.shape[3] + 2 <= 256 and _conv_policy() != "lib")
+
+
+def conv_tc_wanted(x: torch.Tensor, weight: torch.Tensor, stride: int, padding: int) -> bool:
+    """Supported AND selected by the policy for this layer shape."""
+    if not conv_tc_supported(x, weight, stride, padding):
+        return False
+    n, cin, h, w = x.shape
+    return _fprop_native(cin, weight.shape[0], weight.shape[2], n * h * w)
 
 
 def _cl(t: torch.Tensor) -> torch.Tensor:
@@ -185,10 +215,14 @@ class _ConvTC(torch.autograd.Function):
         pad = (k - 1) // 2
         dyc = _cl(dy)
         dx = dw = None
+        n, cin, h, wd = x.shape
         if ctx.needs_input_grad[0]:
-            dx = C.conv_dgrad(dyc, w, 1, pad, -1, 0, 0)
+            if _dgrad_native(cin, w.shape[0], k, n * h * wd):
+                dx = C.conv_dgrad(dyc, w, 1, pad, -1, 0, 0)[0]
+            else:
+                dx = torch.ops.aten.convolution_backward(dyc, x, w, None, [1, 1], [pad, pad], [1, 1], False, [0, 0], 1,
+                                                         [True, False, False])[0]
         if ctx.needs_input_grad[1]:
-            n, cin, h, wd = x.shape
             if _wgrad_native(cin, w.shape[0], k, n * h * wd):
                 dw = C.conv_wgrad(dyc, x, k, 1, pad, 0, 0, 0)
             else:

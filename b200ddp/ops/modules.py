@@ -47,7 +47,7 @@ class Conv2dTC(nn.Conv2d):
         super().__init__(in_channels, out_channels, kernel_size, stride=stride, padding=(kernel_size - 1) // 2, bias=False, **kw)
 
     def _native(self, x: torch.Tensor) -> bool:
-        return Fn.conv_tc_supported(x, self.weight, self.stride[0], self.padding[0]) and self.stride[0] == self.stride[1]
+        return self.stride[0] == self.stride[1] and Fn.conv_tc_wanted(x, self.weight, self.stride[0], self.padding[0])
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if self._native(x):

@@ -210,6 +210,8 @@ class DistributedDataParallel(nn.Module):
             self.reducer = _PyReducer(self._params, self._specs, self.comm, gradient_as_bucket_view,
                                       find_unused_parameters)
         self._callback_queued = False
+        self._comm_stream = None
+        self._buf_pending = None
         self._hook_handles = []
         if self.world_size > 1:   # a single rank has nothing to reduce: no hooks, zero overhead
             for i, p in enumerate(self._params):
@@ -240,6 +242,29 @@ class DistributedDataParallel(nn.Module):
         if bufs:
             self.comm.broadcast_tensors(bufs, src=0)
 
+    def _sync_buffers_after_forward(self) -> None:
+        """Native backend: rank 0's buffers (BatchNorm running statistics) reach every rank on the COMM stream right after
+        the forward pass, overlapped with backward, instead of on the compute stream before the forward pass (stock
+        ``_sync_buffers``).  Training-mode forward never reads the running statistics, so at every forward
+        start each rank still holds "rank 0's buffers as of its previous forward" - the stock contract - but the
+        cross-GPU rendezvous of the broadcast kernel is off the critical path.  It is the first kernel on the comm stream
+        of this iteration on every rank (bucket launches follow in plan order), and ``Reducer::finalize`` joins that
+        stream back into the compute stream."""
+        bufs = [b.data for b in self.module.buffers()]
+        if not bufs:
+            return
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.ExternalStream(self.reducer._c.comm_stream(), device=bufs[0].device)
+        cur = torch.cuda.current_stream(bufs[0].device)
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        self._comm_stream.wait_event(fork)
+        with torch.cuda.stream(self._comm_stream):
+            self.comm.broadcast_tensors(bufs, src=0)
+            done = torch.cuda.Event()
+            done.record(self._comm_stream)
+        self._buf_pending = done
+
     # ---- autograd plumbing -------------------------------------------------------------------
     def _make_hook(self, index: int):
         def hook(param):
@@ -254,12 +279,23 @@ class DistributedDataParallel(nn.Module):
     def _finalize_backward(self) -> None:
         self._callback_queued = False
         self.reducer.finalize()
+        self._buf_pending = None          # finalize joined the comm stream (buffer broadcast included) into the compute stream
 
     def forward(self, *inputs, **kwargs):
-        if self.world_size > 1 and self.require_backward_grad_sync and torch.is_grad_enabled():
+        sync = self.world_size > 1 and self.require_backward_grad_sync and torch.is_grad_enabled()
+        overlap = sync and self.broadcast_buffers and self.backend_name == "b200"
+        if sync:
             self.reducer.reset()
-            self._sync_buffers()
-        return self.module(*inputs, **kwargs)
+            if overlap:
+                if self._buf_pending is not None:       # a forward that was never followed by backward: join its broadcast now
+                    torch.cuda.current_stream().wait_event(self._buf_pending)
+                    self._buf_pending = None
+            else:
+                self._sync_buffers()
+        out = self.module(*inputs, **kwargs)
+        if overlap:
+            self._sync_buffers_after_forward()
+        return out
 
     @contextlib.contextmanager
     def no_sync(self):

@@ -65,6 +65,9 @@ def parse_args():
     p.add_argument("--stock_graph", action="store_true", help="--impl stock: replay the whole stock step (fwd + bwd + DDP/NCCL + clip + SGD) from one CUDA graph")
     p.add_argument("--no_comm", action="store_true", help="diagnostic: N ranks, gradient communication disabled")
     p.add_argument("--profile_range", action="store_true", help="cudaProfilerStart/Stop around the device-timed loop (ncu --profile-from-start off)")
+    p.add_argument("--trace_dir", type=str, default=None, help="after the timed loops: 4 more steps under the CUPTI profiler, one chrome trace per rank "
+                                                                  "(<dir>/rank<r>.json) for tools/trace_digest.py; never a timing source")
+    p.add_argument("--no_broadcast_buffers", action="store_true", help="diagnostic: DDP without the per-step buffer broadcast")
     args = p.parse_args()
     if args.per_gpu_batch is None:
         args.per_gpu_batch = 16 if args.model.startswith("bert") else 32
@@ -216,7 +219,8 @@ def run_ours(args):
     if world > 1:
         model = DistributedDataParallel(model, device_ids=[local_rank], find_unused_parameters=args.find_unused_parameters,
                                         gradient_as_bucket_view=args.gradient_as_bucket_view, backend=backend,
-                                        bucket_cap_mb=args.bucket_cap_mb, wire_dtype=args.wire_dtype)
+                                        bucket_cap_mb=args.bucket_cap_mb, wire_dtype=args.wire_dtype,
+                                        broadcast_buffers=not args.no_broadcast_buffers)
         backend = model.backend_name
         if args.no_comm:
             model.require_backward_grad_sync = False
@@ -366,6 +370,17 @@ def run_ours(args):
                           "d2h_bytes_per_step": e2e["d2h"], "last_loss": e2e["last_loss"],
                           "host_wait_for_batch_ms_per_step": e2e["loader_wait_ms"]}
         emit(out)
+    if args.trace_dir:
+        from torch.profiler import ProfilerActivity, profile
+        os.makedirs(args.trace_dir, exist_ok=True)
+        sync_all()
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+            for i in range(4):
+                x, y = resident[i % len(resident)]
+                step(x, y)
+                sched.step()
+            sync_all()
+        prof.export_chrome_trace(os.path.join(args.trace_dir, f"rank{rank}.json"))
     stream.close()                      # stops the loader's helper thread before interpreter shutdown
     if world > 1:
         try:

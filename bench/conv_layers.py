@@ -140,7 +140,7 @@ def main():
                                     call = lambda i, mode=mode, bn=bn, bo=bo: C.conv_fprop(xs[i % nsets], w, 1, pad, mode, bn, bo, False)[0]   # noqa: E731
                                     e = rel(call(0), y_ref)
                                 else:
-                                    call = lambda i, mode=mode, bn=bn, bo=bo: C.conv_dgrad(dys[i % nsets], w, 1, pad, mode, bn, bo)   # noqa: E731
+                                    call = lambda i, mode=mode, bn=bn, bo=bo: C.conv_dgrad(dys[i % nsets], w, 1, pad, mode, bn, bo)[0]   # noqa: E731
                                     e = rel(call(0), g_ref[0])
                                 torch.cuda.synchronize()
                                 if not (e < 2e-2):

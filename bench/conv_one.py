@@ -40,7 +40,7 @@ def main():
         if a.op == "f":
             C.conv_fprop(x, w, 1, pad, a.mode, a.bn, 0, False)
         elif a.op == "d":
-            C.conv_dgrad(dy, w, 1, pad, a.mode, a.bn, 0)
+            C.conv_dgrad(dy, w, 1, pad, a.mode, a.bn, 0)[0]
         else:
             C.conv_wgrad(dy, x, k, 1, pad, a.split, a.tm, a.tn)
     torch.cuda.synchronize()

@@ -28,12 +28,25 @@ def test_torch_order_matches_stock_layout(name, expected):
 
 @pytest.mark.parametrize("cap,count", [(1, 76), (25, 14), (256, 3)])
 def test_bert_bucket_counts(cap, count):
+    """SURVEY 2.4-K4 layouts of the stock BERT-base tensor list (199 tensors: separate query / key / value), and the planner
+    against torch's on this package's model, whose Q / K / V projection is one stored parameter (151 tensors)."""
+    import torch
     model = build_model("bert-base", with_mlm_head=False)
-    params = list(model.parameters())
-    specs = plan_buckets(_sizes(model), [4] * len(params), bucket_cap_bytes=cap * MiB, order="torch", max_tensors=10 ** 9)
+    stock = []
+    for name, p in model.named_parameters():
+        if ".qkv." in name:
+            stock += [torch.nn.Parameter(torch.empty_like(c)) for c in p.detach().chunk(3, dim=0)]
+        else:
+            stock.append(p)
+    assert len(stock) == 199
+    specs = plan_buckets([p.numel() for p in stock], [4] * len(stock), bucket_cap_bytes=cap * MiB, order="torch", max_tensors=10 ** 9)
     assert len(specs) == count
-    ref = dist._compute_bucket_assignment_by_size(params, [1 * MiB, cap * MiB])[0]
+    ref = dist._compute_bucket_assignment_by_size(stock, [1 * MiB, cap * MiB])[0]
     assert [s.param_indices for s in reversed(specs)] == ref
+    params = list(model.parameters())
+    mine = plan_buckets(_sizes(model), [4] * len(params), bucket_cap_bytes=cap * MiB, order="torch", max_tensors=10 ** 9)
+    ref = dist._compute_bucket_assignment_by_size(params, [1 * MiB, cap * MiB])[0]
+    assert [s.param_indices for s in reversed(mine)] == ref
 
 
 def test_backward_order_first_bucket_small_and_layout_aligned():

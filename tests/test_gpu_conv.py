@@ -48,7 +48,7 @@ def test_forward_and_data_gradient_match_fp32_reference(n, ci, co, k, h, w):
             if bn and (co % bn or ci % bn):
                 continue
             y = C.conv_fprop(x, wt, 1, pad, mode, bn, 0, False)[0]
-            dx = C.conv_dgrad(dy, wt, 1, pad, mode, bn, 0)
+            dx = C.conv_dgrad(dy, wt, 1, pad, mode, bn, 0)[0]
             assert y.shape == y_ref.shape and y.is_contiguous(memory_format=torch.channels_last)
             assert _rel(y, y_ref) < 6e-3, (mode, bn, _rel(y, y_ref))
             assert _rel(dx, dx_ref) < 6e-3, (mode, bn, _rel(dx, dx_ref))
@@ -88,9 +88,10 @@ def test_epilogue_statistics_equal_the_column_sums_of_the_stored_output(n, ci, c
     assert torch.equal(st, C.conv_fprop(x, wt, 1, (k - 1) // 2, -1, 0, 0, True)[1])
 
 
-def test_bottleneck_matches_stock_modules_forward_and_backward():
+def test_bottleneck_matches_stock_modules_forward_and_backward(monkeypatch):
     """Conv2dTC + FusedBatchNormAct2d with statistics from the epilogue vs nn.Conv2d + nn.BatchNorm2d in fp32."""
     import torch.nn as nn
+    monkeypatch.setenv("B200DDP_CONV", "native")
     from b200ddp.models.resnet import Bottleneck
     from b200ddp.utils import to_mixed_bf16
     torch.manual_seed(0)
@@ -113,3 +114,67 @@ def test_bottleneck_matches_stock_modules_forward_and_backward():
         assert _rel(a.weight.grad, b.weight.grad) < 1e-1      # bf16 activations through three BatchNorms vs an fp32 chain
         assert a.weight.grad.stride() == a.weight.stride()
     assert torch.allclose(blk.bn1.running_mean, ref[1].running_mean, atol=2e-2)
+
+
+@pytest.mark.parametrize("n,ci,co,k,h,w", [(4, 64, 256, 1, 56, 56), (3, 128, 128, 3, 28, 28), (2, 64, 64, 3, 56, 56), (5, 1024, 256, 1, 14, 14)])
+def test_data_gradient_epilogue_fusion_addend_and_batchnorm_partial_sums(n, ci, co, k, h, w):
+    """conv_dgrad(+ addend)(+ S1/S2 of the BatchNorm backward that consumes dx) vs the same quantities computed by hand."""
+    from b200ddp import _ext
+    C = _ext.get()
+    x, wt, dy = _mk(n, ci, co, k, h, w)
+    pad = (k - 1) // 2
+    torch.manual_seed(3)
+    addend = torch.randn_like(x)
+    bn_x = torch.randn_like(x)                             # input of the (imaginary) BatchNorm whose output fed this convolution
+    mask_bits = torch.rand(n, h, w, ci, device="cuda") > 0.4
+    packed = (mask_bits.view(-1, ci // 8, 8).to(torch.uint8) << torch.arange(8, device="cuda", dtype=torch.uint8)).sum(-1).to(torch.uint8)
+    mean = torch.randn(ci, device="cuda") * 0.1
+    rstd = torch.rand(ci, device="cuda") + 0.5
+    stats = torch.stack([mean, rstd]).contiguous()
+    plain = C.conv_dgrad(dy, wt, 1, pad, -1, 0, 0)[0]
+    dx, part = C.conv_dgrad(dy, wt, 1, pad, -1, 0, 0, 0, addend, bn_x, packed.contiguous(), stats)
+    ref = (plain.float() + addend.float()).to(torch.bfloat16)
+    assert _rel(dx, ref) < 1e-2
+    d2 = dx.permute(0, 2, 3, 1).reshape(-1, ci).float()
+    m2 = mask_bits.reshape(-1, ci).float()
+    xh = (bn_x.permute(0, 2, 3, 1).reshape(-1, ci).float() - mean) * rstd
+    s1, s2 = (d2 * m2).sum(0), (d2 * m2 * xh).sum(0)
+    assert part.shape[0] == 2 and part.shape[2] == ci
+    assert torch.allclose(part[0].sum(0), s1, rtol=2e-3, atol=0.5), float((part[0].sum(0) - s1).abs().max())
+    assert torch.allclose(part[1].sum(0), s2, rtol=2e-3, atol=0.5), float((part[1].sum(0) - s2).abs().max())
+    only_add = C.conv_dgrad(dy, wt, 1, pad, -1, 0, 0, 0, addend)[0]
+    assert torch.equal(only_add, dx)
+
+
+@pytest.mark.parametrize("with_downsample", [False, True])
+def test_fused_bottleneck_node_equals_the_per_layer_composition(with_downsample, monkeypatch):
+    """ops/bottleneck.py (one autograd node, epilogue-fused backward) vs the same block composed of per-layer autograd ops."""
+    import copy
+    import torch.nn as nn
+    from b200ddp.models.resnet import Bottleneck
+    from b200ddp.ops import FusedBatchNormAct2d, PointwiseConv2d
+    from b200ddp.utils import to_mixed_bf16
+    monkeypatch.setenv("B200DDP_CONV", "native")
+    torch.manual_seed(0)
+    inpl = 64 if with_downsample else 256
+    ds = nn.Sequential(PointwiseConv2d(64, 256), FusedBatchNormAct2d(256)) if with_downsample else None
+    a = to_mixed_bf16(Bottleneck(inpl, 64, 1, ds).cuda()).to(memory_format=torch.channels_last)
+    b = copy.deepcopy(a)
+    x = torch.randn(8, inpl, 28, 28, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    g = torch.randn(8, 256, 28, 28, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    monkeypatch.setenv("B200DDP_BLOCK_FUSE", "1")
+    ya = a(xa)
+    ya.backward(g)
+    monkeypatch.setenv("B200DDP_BLOCK_FUSE", "0")
+    yb = b(xb)
+    yb.backward(g)
+    assert ya.grad_fn.__class__.__name__.startswith("_BottleneckFn")
+    assert _rel(ya, yb) < 1e-3
+    assert _rel(xa.grad, xb.grad) < 3e-2
+    for (n, p), q in zip(a.named_parameters(), b.parameters()):
+        assert p.grad is not None and q.grad is not None, n
+        assert _rel(p.grad, q.grad) < 3e-2, (n, _rel(p.grad, q.grad))
+        assert p.grad.stride() == p.stride(), n
+    for (n, u), v in zip(a.named_buffers(), b.buffers()):
+        assert torch.allclose(u.float(), v.float(), atol=1e-3), n

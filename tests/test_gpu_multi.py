@@ -116,13 +116,22 @@ def _check_collectives(rank, world):
         assert torch.equal(m.cpu(), b), (rank, b.shape)
     assert torch.equal(view.cpu(), torch.arange(1000.0))
     stage("stress")
-    # stress the barrier protocol: many back-to-back tiny collectives
-    t = torch.ones(3, device=dev)
-    for _ in range(200):
-        comm.allreduce_([t], wire="fp32", algo="one_shot", scale=1.0 / world)
+    # stress the barrier protocol: 1000 back-to-back collectives of odd sizes, cycling through every algorithm, checked on
+    # the device against the expected sum (no host sync inside the loop, so launches of consecutive epochs overlap)
+    sizes = [3, 1, 165, 4099, 7, 65537, 33, 1023]
+    bad = torch.zeros((), device=dev)
+    bufs = {n: torch.empty(n, device=dev) for n in sizes}
+    for it in range(1000):
+        n = sizes[it % len(sizes)]
+        algo = algos[it % len(algos)] if n <= 4099 else ("nvls" if comm.nvls and it % 2 else "two_shot")
+        t = bufs[n]
+        t.fill_(float(rank + 1 + it % 5))
+        comm.allreduce_([t], wire="fp32", algo=algo, scale=1.0)
+        expect = float(sum(r + 1 + it % 5 for r in range(world)))
+        bad += (t - expect).abs().max()
     torch.cuda.synchronize()
     comm.check()
-    assert torch.allclose(t, torch.ones_like(t))
+    assert float(bad) == 0.0, float(bad)
 
 
 def test_peer_collectives(free_port):
@@ -233,6 +242,89 @@ def _check_ddp_mlp_bf16_and_unused(rank, world):
 
 def test_ddp_bf16_and_unused_parameters(free_port):
     _spawn(_check_ddp_mlp_bf16_and_unused, free_port)
+
+
+# --------------------------------------------------------------------------------------------------
+def _check_one_shot_ownership(rank, world):
+    """Regression for the one-shot allreduce: every phase must give a vector to the same block, else a block reads staging
+    another block has not packed yet (stale gradients of the previous launch).  Geometry of the ResNet-50 fp32 BatchNorm
+    bucket (208 KB: 7 blocks, slices misaligned with the block stride for every world size), block start skew provoked
+    by a long-running kernel that occupies the SMs, values that change every launch so stale data cannot pass."""
+    from b200ddp.parallel.peer import PeerCollectives
+    dev = torch.device("cuda", rank)
+    comm = PeerCollectives.get(None, dev, min_bytes=64 << 20)
+    algos = ["one_shot"] + (["nvls_one_shot"] if comm.nvls else [])
+    n = 53224                                                 # 207.9 KB fp32: V = 13306 vectors, not a multiple of world * 7 * 256
+    hog = torch.empty(64 << 20, device=dev)
+    t = torch.empty(n, device=dev)
+    idx = torch.arange(n, device=dev, dtype=torch.float32)
+    bad = torch.zeros((), device=dev)
+    for it in range(300):
+        for algo in algos:
+            if it % 3 == rank % 3:
+                hog.normal_()                                 # staggers this rank's comm-kernel blocks against its peers'
+            t.copy_(idx * 1e-3 + float(it * world + rank))
+            comm.allreduce_([t], wire="fp32", algo=algo, scale=1.0, blocks=7)
+            expect = idx * 1e-3 * world + float(sum(it * world + r for r in range(world)))
+            bad += (t - expect).abs().max()
+    torch.cuda.synchronize()
+    comm.check()
+    assert float(bad) < 1e-2 * 300 * len(algos), float(bad)
+
+
+def test_one_shot_allreduce_block_ownership_under_skew(free_port):
+    _spawn(_check_one_shot_ownership, free_port)
+
+
+# --------------------------------------------------------------------------------------------------
+def _check_ddp_resnet50(rank, world):
+    """ResNet-50, bf16 weights + fp32 BatchNorm (mixed bf16 / fp32 buckets, NVLS two-shot on the large ones, one-shot on the
+    BatchNorm bucket, bounded tail bucket, buffer broadcast on the comm stream, whole step replayed from a CUDA graph)
+    against stock torch DDP + NCCL driving the SAME model class: parameters and running statistics agree within bf16
+    tolerance after 10 steps and every rank holds bit-identical state."""
+    from b200ddp.engine.step import TrainStep
+    from b200ddp.models import build_model
+    from b200ddp.ops import MSELoss
+    from b200ddp.optim import FusedSGD
+    from b200ddp.parallel import DistributedDataParallel
+    from b200ddp.utils import to_mixed_bf16
+    dev = torch.device("cuda", rank)
+
+    def make(seed):
+        torch.manual_seed(seed)
+        return to_mixed_bf16(build_model("resnet50").to(dev)).to(memory_format=torch.channels_last)
+    ours, stock = make(1000 + rank), make(1000)              # rank-dependent init on our side: the wrap must broadcast rank 0's
+    ddp = DistributedDataParallel(ours, device_ids=[rank], backend="b200")
+    ref = nn.parallel.DistributedDataParallel(stock, device_ids=[rank])
+    kinds = {str(p.dtype) for p in ours.parameters()}
+    assert kinds == {"torch.bfloat16", "torch.float32"} and len(ddp._specs) >= 5
+    opt = FusedSGD(ours.parameters(), lr=0.01, max_grad_norm=1000.0)
+    ropt = FusedSGD(stock.parameters(), lr=0.01, max_grad_norm=1000.0)
+    step = TrainStep(ddp, MSELoss(), opt, dev, use_graph=True)
+    rstep = TrainStep(ref, MSELoss(), ropt, dev, use_graph=False)
+    for i in range(10):
+        g = torch.Generator().manual_seed(rank * 131 + i)
+        x = torch.randn(8, 3, 96, 96, generator=g).to(dev, torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        y = torch.randn(8, 1000, generator=g).to(dev, torch.bfloat16)
+        step(x, y)
+        rstep(x, y)
+    torch.cuda.synchronize()
+    ddp.comm.check()
+    assert step.graph is not None
+    for (n, a), b in zip(ours.named_parameters(), stock.parameters()):
+        assert torch.allclose(a.float(), b.float(), atol=3e-2, rtol=3e-2), (n, float((a.float() - b.float()).abs().max()))
+    for (n, a), b in zip(ours.named_buffers(), stock.buffers()):
+        assert torch.allclose(a.float(), b.float(), atol=3e-2, rtol=3e-2), (n, float((a.float() - b.float()).abs().max()))
+    flat = torch.cat([p.detach().float().reshape(-1) for p in list(ours.parameters()) + list(ours.buffers())])
+    gathered = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    assert all(torch.equal(t, gathered[0]) for t in gathered), "ranks diverged"
+    stats = ddp.ddp_stats()
+    assert stats["buckets_launched"] >= len(ddp._specs)
+
+
+def test_ddp_resnet50_matches_stock_ddp(free_port):
+    _spawn(_check_ddp_resnet50, free_port)
 
 
 # --------------------------------------------------------------------------------------------------

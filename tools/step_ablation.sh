@@ -1,11 +1,12 @@
-cd /root/repo
+#!/bin/bash
+cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_conv.py -m gpu -x -q > gpurun_out/test_conv.log 2>&1; echo "conv tests rc=$?"; tail -n 8 gpurun_out/test_conv.log
+timeout 400 python -m pytest tests/test_gpu_conv.py tests/test_gpu_step.py -m gpu -x -q > gpurun_out/test_conv.log 2>&1; echo "conv tests rc=$?"; tail -n 12 gpurun_out/test_conv.log
 B="python bench.py --gpus 1 --steps 40 --warmup 8 --skip_e2e"
-for cfg in "native:auto" "native:lib" "native:native" "lib:lib"; do
-  c=${cfg%%:*}; w=${cfg##*:}
-  B200DDP_CONV=$c B200DDP_CONV_WGRAD=$w timeout 200 $B > gpurun_out/step_conv_${c}_wgrad_${w}.json 2> gpurun_out/step_conv_${c}_wgrad_${w}.err; echo "conv=$c wgrad=$w rc=$?"
-  python - gpurun_out/step_conv_${c}_wgrad_${w}.json <<'PY'
+run() {
+  local tag=$1; shift
+  env "$@" timeout 200 $B > gpurun_out/step_$tag.json 2> gpurun_out/step_$tag.err; echo "$tag rc=$?"
+  python - gpurun_out/step_$tag.json <<'PY'
 import json, sys
 try:
     d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
@@ -13,4 +14,8 @@ try:
 except Exception as e:
     print("   no result:", e)
 PY
-done
+}
+run fused_auto B200DDP_CONV=native B200DDP_CONV_WGRAD=auto B200DDP_BLOCK_FUSE=1
+run fused_wlib B200DDP_CONV=native B200DDP_CONV_WGRAD=lib B200DDP_BLOCK_FUSE=1
+run unfused_wlib B200DDP_CONV=native B200DDP_CONV_WGRAD=lib B200DDP_BLOCK_FUSE=0
+run lib B200DDP_CONV=lib B200DDP_CONV_WGRAD=lib
