@@ -146,8 +146,9 @@ def _fprop_native(cin: int, cout: int, k: int, pixels: int) -> bool:
         return True
     if mode == "lib":
         return False
-    # measured wins (bench/conv_layers.py, batch 32): the memory-bound 64 -> 256 expansion of layer1 (14.2 us vs 18.2 us)
-    return k == 1 and cin == 64 and cout >= 256 and pixels >= 50176
+    # No layer shape wins inside the training step yet: the 64 -> 256 expansion of layer1 is faster in isolation (14.2 us vs
+    # 18.2 us, cold L2) but the step with it is 5.08 ms vs 4.95 ms (gpurun_out/step1_{auto,lib}.json), so `auto` == library.
+    return False
 
 
 def _dgrad_native(cin: int, cout: int, k: int, pixels: int) -> bool:

@@ -14,6 +14,8 @@ relies on it).  ``plan_buckets(order="torch")`` gives the stock layout + launch 
 """
 from __future__ import annotations
 
+import os
+
 from dataclasses import dataclass, field
 from typing import Dict, Hashable, List, Optional, Sequence, Tuple
 
@@ -101,6 +103,8 @@ def plan_buckets(numels: Sequence[int], elem_sizes: Sequence[int], keys: Optiona
     n = len(numels)
     if keys is None:
         keys = [0] * n
+    if os.environ.get("B200DDP_TAIL_BUCKET_MB"):            # diagnostics: bound of the bucket that completes last
+        tail_bucket_bytes = int(float(os.environ["B200DDP_TAIL_BUCKET_MB"]) * MiB)
     if order == "torch":
         walk = list(range(n))
     elif ready_order is not None:

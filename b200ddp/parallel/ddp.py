@@ -332,6 +332,8 @@ class DistributedDataParallel(nn.Module):
         self._specs = plan_buckets([p.numel() for p in self._params], [p.element_size() for p in self._params],
                                    keys, self.bucket_cap_bytes, self.first_bucket_bytes, ready_order=order)
         if hasattr(self.reducer, "rebuilt"):
+            self._comm_stream = None                     # belongs to the reducer that is about to be destroyed
+            self._buf_pending = None
             self.reducer = self.reducer.rebuilt(self._specs)
         else:
             self.reducer = _PyReducer(self._params, self._specs, self.comm, self.gradient_as_bucket_view,
