@@ -257,7 +257,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   py::class_<Reducer>(m, "Reducer")
       .def(py::init([](PeerArena& arena, std::vector<BucketPlan> plans, int num_params, int algo,
                        int max_blocks, int tail_blocks, long long one_shot_max_bytes, bool as_view, bool find_unused, double extra_scale,
-                       double timeout_s) {
+                       double timeout_s, int serial, int wide_blocks, long long tail_one_shot_max_bytes) {
              ReducerOptions o;
              o.algo = algo;
              o.max_blocks = max_blocks;
@@ -267,6 +267,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
              o.find_unused = find_unused;
              o.extra_scale = (float)extra_scale;
              o.timeout_s = timeout_s;
+             o.serial = serial;
+             o.wide_blocks = wide_blocks;
+             o.tail_one_shot_max_bytes = tail_one_shot_max_bytes;
              return std::make_unique<Reducer>(&arena, std::move(plans), num_params, o);
            }),
            py::keep_alive<1, 2>())
@@ -281,6 +284,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def("read_used_flags", &Reducer::read_used_flags)
       .def("synchronize", &Reducer::synchronize)
       .def("comm_stream", &Reducer::comm_stream)
+      .def("runs_inline", &Reducer::runs_inline)
+      .def("note_comm_stream_used", &Reducer::note_comm_stream_used)
+      .def("set_eager_inline", &Reducer::set_eager_inline)
       .def("error_code", &Reducer::error_code)
       .def_readonly("launches", &Reducer::launches)
       .def_readonly("bytes_on_wire", &Reducer::bytes_on_wire)

@@ -8,6 +8,7 @@
 //   others   : pull 16-byte vectors from the source arena over NVLink (or read their local copy
 //              after a multicast) and scatter straight into their own tensors - no flat temp
 //   [peer barrier] so the next chunk may reuse the staging region
+#include <cstdlib>
 #include "comm_kernels.cuh"
 #include "comm.h"
 
@@ -26,6 +27,7 @@ __global__ void __launch_bounds__(kCommThreads, kCommMinCtasPerSm) peer_broadcas
   __shared__ uint32_t offs[kMaxBucketTensors + 1];
   const CommCtx& c = a.ctx;
   const int count = a.tab.count;
+  if (a.src_rank < 0) return;                          // diagnostics (B200DDP_DEBUG_BCAST_NOOP): same node, no work
   for (int i = threadIdx.x; i < count; i += blockDim.x) { slots[i] = a.tab.t[i]; offs[i] = a.tab.t[i].off; }
   if (threadIdx.x == 0) offs[count] = a.tab.data_elems;
   __shared__ uint32_t s_epoch;
@@ -88,7 +90,8 @@ void launch_peer_broadcast(const CommCtx& ctx, const BucketTable& tab, size_t st
   BcArgs args;
   args.ctx = ctx;
   args.stage_off = stage_off;
-  args.src_rank = src_rank;
+  static const bool noop = [] { const char* e = getenv("B200DDP_DEBUG_BCAST_NOOP"); return e && atoi(e) != 0; }();
+  args.src_rank = noop ? -1 : src_rank;
   args.use_mc = (use_multicast && ctx.mc_base != nullptr) ? 1 : 0;
   args.tab = tab;
   peer_broadcast_kernel<<<blocks, kCommThreads, 0, stream>>>(args);

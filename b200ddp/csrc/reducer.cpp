@@ -83,7 +83,12 @@ Reducer::Reducer(PeerArena* arena, std::vector<BucketPlan> plans, int num_params
     int algo = opt_.algo;
     if (algo == kAlgoAuto) {
       const bool mc = arena_->has_multicast();
+      // The bucket that completes at the very end of backward is pure exposed latency: with in-switch reduction every rank
+      // simply multimem.ld_reduce's the whole (<= tail_one_shot_max_bytes) bucket - one rendezvous, no second exchange phase.
+      const bool is_tail = p.tail || b + 1 == plans_.size();
       if ((long long)wire_bytes <= opt_.one_shot_max_bytes) algo = mc ? kAlgoNvlsOneShot : kAlgoOneShot;
+      else if (is_tail && mc && (long long)wire_bytes <= opt_.tail_one_shot_max_bytes) algo = kAlgoNvlsOneShot;
+      else if (is_tail && !mc && ctx_.world == 2 && (long long)wire_bytes <= opt_.tail_one_shot_max_bytes) algo = kAlgoOneShot;
       else algo = mc ? kAlgoNvls : kAlgoTwoShot;
     }
     if (algo == kAlgoNvls && !arena_->has_multicast()) algo = kAlgoTwoShot;
@@ -94,6 +99,8 @@ Reducer::Reducer(PeerArena* arena, std::vector<BucketPlan> plans, int num_params
     long long blocks = (per_rank + kCommThreads * 8 - 1) / (kCommThreads * 8);
     const int cap = (p.tail || b + 1 == plans_.size()) ? opt_.tail_blocks : opt_.max_blocks;
     s.blocks = (int)std::max(1LL, std::min<long long>(blocks, std::min(cap, kMaxCommBlocks)));
+    const long long wide = (per_rank + kCommThreads * 2 - 1) / (kCommThreads * 2);
+    s.blocks_wide = (int)std::max(1LL, std::min<long long>(wide, std::min(opt_.wide_blocks, kMaxCommBlocks)));
     B200_CUDA_CHECK(cudaEventCreateWithFlags(&s.ready_event, cudaEventDisableTiming));
     B200_CUDA_CHECK(cudaHostAlloc((void**)&s.flags_host, sizeof(float) * kMaxBucketTensors, cudaHostAllocMapped));
     B200_CUDA_CHECK(cudaHostGetDevicePointer((void**)&s.flags_dev, s.flags_host, 0));
@@ -153,8 +160,20 @@ bool nvtx_enabled() {
 }
 }  // namespace
 
+bool Reducer::runs_inline(uintptr_t compute_stream) const {
+  if (opt_.serial == 0 || opt_.serial == 1) return opt_.serial != 0;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(reinterpret_cast<cudaStream_t>(compute_stream), &st) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+  const bool capturing = st == cudaStreamCaptureStatusActive;
+  if (opt_.serial == 3) return capturing;                 // diagnostics: the opposite assignment
+  return capturing ? false : eager_inline_;               // captured launches fork onto the comm stream; eager ones as configured
+}
+
 void Reducer::launch_bucket(int b, cudaStream_t compute) {
   BucketState& s = buckets_[b];
+  const bool inline_run = runs_inline(reinterpret_cast<uintptr_t>(compute));
+  cudaStream_t where = inline_run ? compute : comm_stream_;
+  const int blocks = inline_run ? s.blocks_wide : s.blocks;
   const bool mark = nvtx_enabled();
   if (mark) {
     const std::string label = "b200ddp.bucket" + std::to_string(b) + " " +
@@ -162,16 +181,22 @@ void Reducer::launch_bucket(int b, cudaStream_t compute) {
                               "B algo" + std::to_string(s.algo) + " x" + std::to_string(s.blocks);
     nvtxRangePushA(label.c_str());
   }
-  B200_CUDA_CHECK(cudaEventRecord(s.ready_event, compute));
-  B200_CUDA_CHECK(cudaStreamWaitEvent(comm_stream_, s.ready_event, 0));
+  if (!inline_run) {
+    B200_CUDA_CHECK(cudaEventRecord(s.ready_event, compute));
+    B200_CUDA_CHECK(cudaStreamWaitEvent(comm_stream_, s.ready_event, 0));
+    used_comm_stream_ = true;
+  }
   float* sq = sq_partials_ ? sq_partials_ + (size_t)b * sq_stride_ : nullptr;
   const float scale = opt_.extra_scale / (float)ctx_.world;
   const bool scatter = !opt_.as_view;
   CommCtx ctx = ctx_;
   ctx.pad_off = (size_t)(2 + b) * kPadSetBytes;
-  launch_bucket_allreduce(ctx, s.table, s.stage_off, (DType)plans_[b].grad_dtype, (DType)plans_[b].wire_dtype, s.algo, s.blocks,
+  static const int debug_mode = [] { const char* e = std::getenv("B200DDP_DEBUG_BUCKET"); return e ? std::atoi(e) : 0; }();
+  if (debug_mode == 1) { s.launched = true; ++launches; if (mark) nvtxRangePop(); return; }                 // diagnostics: bookkeeping only
+  if (debug_mode == 2) { B200_CUDA_CHECK(cudaMemsetAsync(arena_->error_word_dev() + 0, 0, 0, where)); }   // (no-op placeholder)
+  launch_bucket_allreduce(ctx, s.table, s.stage_off, (DType)plans_[b].grad_dtype, (DType)plans_[b].wire_dtype, s.algo, blocks,
                           (opt_.as_view || opt_.find_unused) ? s.flat_out : nullptr, sq,
-                          opt_.find_unused ? s.flags_dev : nullptr, scale, scatter, comm_stream_);
+                          opt_.find_unused ? s.flags_dev : nullptr, scale, scatter, where);
   if (mark) nvtxRangePop();
   s.launched = true;
   ++launches;
@@ -195,8 +220,11 @@ int Reducer::finalize(uintptr_t compute_stream) {
   for (auto& s : buckets_)
     if (!s.launched) s.pending = 0;   // missing tensors keep ptr == nullptr: zeros + cleared flag
   launch_in_order(compute);
-  B200_CUDA_CHECK(cudaEventRecord(done_event_, comm_stream_));
-  B200_CUDA_CHECK(cudaStreamWaitEvent(compute, done_event_, 0));
+  if (used_comm_stream_) {
+    B200_CUDA_CHECK(cudaEventRecord(done_event_, comm_stream_));
+    B200_CUDA_CHECK(cudaStreamWaitEvent(compute, done_event_, 0));
+    used_comm_stream_ = false;
+  }
   first_iter_ = false;
   ++iterations;
   return missing;

@@ -43,10 +43,19 @@ struct ReducerOptions {
   int max_blocks = 24;        // CTAs for buckets that overlap with the rest of backward (light: see comm_kernels.cuh)
   int tail_blocks = 96;       // CTAs for the last bucket of the plan: nothing is left to overlap with, latency is exposed
   long long one_shot_max_bytes = 256 * 1024;
+  long long tail_one_shot_max_bytes = 8ll << 20;   // tail bucket: single-rendezvous algorithm up to this wire size
   bool as_view = false;
   bool find_unused = false;
   float extra_scale = 1.0f;
   double timeout_s = 30.0;
+  // Where the bucket kernels run.  -1 (default): launches recorded into a CUDA graph fork onto the comm stream (they overlap the
+  // rest of backward when the graph replays); launches issued eagerly follow set_eager_inline(): on the comm stream for an
+  // eager training loop, IN LINE on the compute stream for the few eager warm-up steps of a graph-captured loop.  Reason,
+  // measured (profiles/ddp_timeline.md): once a THIRD stream of the process has executed work, every later graph replay pays
+  // ~0.4 us at each of its ~430 kernel boundaries (+0.17 ms per ResNet-50 step, more than the link time of the whole
+  // gradient exchange); default stream + capture stream are two.  0 / 1 force comm stream / in line everywhere.
+  int serial = -1;
+  int wide_blocks = 296;
 };
 
 class Reducer {
@@ -67,6 +76,10 @@ class Reducer {
   std::vector<float> read_used_flags(int b);   // syncs the comm stream; only for the unused-param path
   void synchronize();
   uintptr_t comm_stream() const { return reinterpret_cast<uintptr_t>(comm_stream_); }
+  // true if bucket kernels launched from `compute_stream` right now would run in line (see ReducerOptions::serial)
+  bool runs_inline(uintptr_t compute_stream) const;
+  void note_comm_stream_used() { used_comm_stream_ = true; }
+  void set_eager_inline(bool on) { eager_inline_ = on; }
   int error_code() const { return arena_->check_error(); }
 
   long long launches = 0, bytes_on_wire = 0, iterations = 0;
@@ -79,7 +92,7 @@ class Reducer {
     void* flat_out = nullptr;
     float* flags_host = nullptr;  // pinned, mapped
     float* flags_dev = nullptr;
-    int pending = 0, blocks = 1, algo = kAlgoTwoShot;
+    int pending = 0, blocks = 1, blocks_wide = 1, algo = kAlgoTwoShot;
     bool launched = false;
     cudaEvent_t ready_event = nullptr;
   };
@@ -100,6 +113,8 @@ class Reducer {
   int next_bucket_ = 0;
   bool active_ = false;
   bool first_iter_ = true;
+  bool eager_inline_ = false;       // see ReducerOptions::serial
+  bool used_comm_stream_ = false;   // this backward pass forked onto the comm stream: finalize must join it
 };
 
 }  // namespace b200

@@ -31,6 +31,8 @@ class TrainStep:
         self.target_transform = target_transform
         self.use_graph = bool(use_graph) and self.device.type == "cuda"
         self.graph_warmup = graph_warmup
+        if self.use_graph and hasattr(model, "set_graph_captured_loop"):
+            model.set_graph_captured_loop(True)
         # static loss scaling (the reference's --loss_scale, ddp.py:179/307): the loss is multiplied before backward and the
         # optimizer divides the gradients again inside the fused kernel (grad_scale); bf16 needs none, so the default is 1
         self.loss_scale = float(loss_scale) if loss_scale and loss_scale > 0 else 1.0

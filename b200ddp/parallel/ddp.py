@@ -25,6 +25,7 @@ Native design:
 from __future__ import annotations
 
 import contextlib
+import os
 from typing import List, Optional
 
 import torch
@@ -253,9 +254,13 @@ class DistributedDataParallel(nn.Module):
         bufs = [b.data for b in self.module.buffers()]
         if not bufs:
             return
+        cur = torch.cuda.current_stream(bufs[0].device)
+        if self.reducer._c.runs_inline(cur.cuda_stream):
+            # captured step: everything stays one linear chain on the compute stream (see ReducerOptions::serial)
+            self.comm.broadcast_tensors(bufs, src=0)
+            return
         if self._comm_stream is None:
             self._comm_stream = torch.cuda.ExternalStream(self.reducer._c.comm_stream(), device=bufs[0].device)
-        cur = torch.cuda.current_stream(bufs[0].device)
         fork = torch.cuda.Event()
         fork.record(cur)
         self._comm_stream.wait_event(fork)
@@ -263,6 +268,7 @@ class DistributedDataParallel(nn.Module):
             self.comm.broadcast_tensors(bufs, src=0)
             done = torch.cuda.Event()
             done.record(self._comm_stream)
+        self.reducer._c.note_comm_stream_used()
         self._buf_pending = done
 
     # ---- autograd plumbing -------------------------------------------------------------------
@@ -307,6 +313,14 @@ class DistributedDataParallel(nn.Module):
         finally:
             self.require_backward_grad_sync = previous
 
+    def set_graph_captured_loop(self, on: bool = True) -> None:
+        """Tell the reducer that the training step will be replayed from a CUDA graph: its few eager warm-up steps then
+        launch the communication kernels in line on the compute stream instead of on the comm stream (a third live stream
+        slows every later graph replay down, see ``ReducerOptions::serial``); captured launches still fork and overlap."""
+        self._graph_loop = bool(on)
+        if hasattr(self.reducer, "_c") and hasattr(self.reducer._c, "set_eager_inline"):
+            self.reducer._c.set_eager_inline(self._graph_loop)
+
     # ---- introspection -----------------------------------------------------------------------
     def bucket_sizes_mib(self) -> List[float]:
         return [round(sum(n * self._params[i].element_size() for i, n in zip(s.param_indices, s.numels)) / MiB, 2)
@@ -335,6 +349,8 @@ class DistributedDataParallel(nn.Module):
             self._comm_stream = None                     # belongs to the reducer that is about to be destroyed
             self._buf_pending = None
             self.reducer = self.reducer.rebuilt(self._specs)
+            if getattr(self, "_graph_loop", False):
+                self.set_graph_captured_loop(True)
         else:
             self.reducer = _PyReducer(self._params, self._specs, self.comm, self.gradient_as_bucket_view,
                                       self.find_unused_parameters)

@@ -229,8 +229,11 @@ class NativeReducer:
         self._arena_mark = comm.arena.used()
         self._ctor = dict(wire_dtype=wire_dtype, algo=algo, max_blocks=max_blocks)
         one_shot_max = int(os.environ.get("B200DDP_ONE_SHOT_MAX_KB", "256")) * 1024
+        serial = int(os.environ.get("B200DDP_DDP_SERIAL", "-1"))       # -1: in line under CUDA-graph capture, overlapped otherwise
+        wide = int(os.environ.get("B200DDP_WIDE_BLOCKS", "296"))
         self._c = C.Reducer(comm.arena, plans, len(params), _ALGO[algo], blocks, comm.tail_blocks, one_shot_max, gradient_as_bucket_view,
-                            find_unused, 1.0, comm.timeout_s)
+                            find_unused, 1.0, comm.timeout_s, serial, wide,
+                            int(float(os.environ.get("B200DDP_TAIL_ONE_SHOT_MAX_MB", "8")) * MiB))
         device = params[0].device
         self.flat_out: List[Optional[torch.Tensor]] = []
         self.views: List[List[torch.Tensor]] = []
