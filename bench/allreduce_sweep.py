@@ -83,9 +83,10 @@ def main():
                 (["nvls_one_shot"] if comm.nvls and size <= (4 << 20) else [])
         for wire in ("fp32", "bf16"):
             for algo in algos:
-                for blocks in [int(b) for b in args.blocks.split(",")]:
-                    if (size < 65536 and blocks > 8) or (size >= (16 << 20) and blocks < 32):
-                        continue
+                cand = sorted({int(b) for b in args.blocks.split(",")})
+                keep = [b for b in cand if not ((size < 65536 and b > 8) or (size >= (16 << 20) and b < 32))] or \
+                       ([cand[0]] if size < 65536 else [cand[-1]])
+                for blocks in keep:
 
                     def ours():
                         comm.allreduce_([bufs[state["i"] % rot]], wire=wire, algo=algo, blocks=blocks); state["i"] += 1

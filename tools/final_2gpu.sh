@@ -1,21 +1,15 @@
 #!/bin/bash
+# 2-GPU acceptance: transport + DDP tests at world 2, then one CUPTI-traced run of the default configuration for the
+# per-rank timeline (profiles/ddp_timeline_r2.md).  A traced run is never a timing source.
 cd "$(dirname "$0")/.."
-N=2
-mkdir -p gpurun_out
-O=gpurun_out
-echo "== multi tests"; timeout 400 python -m pytest tests/test_gpu_multi.py -m gpu -x -q > $O/test_multi_$N.log 2>&1; echo "multi tests rc=$?"; tail -n 3 $O/test_multi_$N.log
-for impl in ours reference; do
-  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29641 \
-     bench.py --impl $impl --gpus $N --steps 40 --warmup 8 > $O/bench_${impl}_$N.json 2> $O/bench_${impl}_$N.err
-  echo "bench $impl rc=$?"; grep '^{' $O/bench_${impl}_$N.json | cut -c1-420
-done
-for impl in ours stock; do
-  timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29642 \
-     bench.py --impl $impl --model bert-base --gpus $N --steps 20 --warmup 6 --skip_e2e --bucket_cap_mb 25 > $O/bert_${impl}_$N.json 2> $O/bert_${impl}_$N.err
-  echo "bert $impl rc=$?"; grep '^{' $O/bert_${impl}_$N.json | cut -c1-300
-done
-timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29643 \
-   bench.py --model foo --gpus $N --steps 200 --warmup 20 > $O/bench_foo_ours_$N.json 2> $O/bench_foo_ours_$N.err; echo "foo ours rc=$?"; grep '^{' $O/bench_foo_ours_$N.json | cut -c1-300
-timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29644 \
-   bench.py --impl reference --model foo --gpus $N --steps 200 --warmup 20 > $O/bench_foo_ref_$N.json 2> $O/bench_foo_ref_$N.err; echo "foo ref rc=$?"; grep '^{' $O/bench_foo_ref_$N.json | cut -c1-300
-tail -n 4 $O/bert_ours_$N.err | cut -c1-300
+N=2; O=gpurun_out; mkdir -p $O
+timeout 400 python -m pytest tests/test_gpu_multi.py tests/test_gpu_data_parallel.py -m gpu -q > $O/test_multi_2.log 2>&1; echo "multi tests (world 2) rc=$? : $(tail -n 1 $O/test_multi_2.log)"
+grep -n "AssertionError\|^E  " $O/test_multi_2.log | head -8
+R="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29611 bench.py --gpus $N --warmup 8 --skip_e2e"
+rm -rf $O/trace_ddp_r2_$N $O/trace_ddp_r2_nocomm_$N
+timeout 200 $R --steps 20 --trace_dir $O/trace_ddp_r2_$N > $O/traced_r2.json 2> $O/traced_r2.err; echo "traced rc=$?"
+timeout 200 $R --steps 20 --no_comm --trace_dir $O/trace_ddp_r2_nocomm_$N > $O/traced_r2_nocomm.json 2> $O/traced_r2_nocomm.err; echo "traced nocomm rc=$?"
+python tools/trace_digest.py $O/trace_ddp_r2_$N --label "$N GPUs, round-2 default" > $O/ddp_timeline_r2_$N.md 2>&1
+python tools/trace_diff.py $O/trace_ddp_r2_$N/rank0.json $O/trace_ddp_r2_nocomm_$N/rank0.json > $O/trace_diff_r2_$N.txt 2>&1
+head -12 $O/trace_diff_r2_$N.txt
+grep -n "exposed tail\|bucket_allreduce\|peer_broadcast" $O/ddp_timeline_r2_$N.md | head -20
