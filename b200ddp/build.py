@@ -22,7 +22,7 @@ BUILD = PKG / "_build"
 EXT_NAME = "_C"
 
 CUDA_SOURCES = ["allreduce.cu", "broadcast.cu", "optim.cu", "loss.cu", "layernorm.cu", "linear_small.cu", "input.cu",
-                "gemm_tcgen05.cu", "batchnorm.cu", "pool.cu", "conv_tcgen05.cu", "conv_wgrad_tcgen05.cu"]
+                "gemm_tcgen05.cu", "batchnorm.cu", "pool.cu", "conv_tcgen05.cu", "conv_wgrad_tcgen05.cu", "conv_stem.cu"]
 CPP_SOURCES = ["peer_mem.cpp", "reducer.cpp", "bindings.cpp"]
 
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]

@@ -572,6 +572,89 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     return dw;
   }, py::arg("dy"), py::arg("x"), py::arg("ksize"), py::arg("stride") = 1, py::arg("pad") = 0, py::arg("split") = 0,
      py::arg("tile_m") = 0, py::arg("tile_n") = 0);
+  // strided 7x7 stem (3 -> 64 channels, stride 2, padding 3) on the tcgen05 tap-GEMM through an overlapping-window tensor map
+  m.def("stem_conv_supported", [](int H, int W) { StemGeom g; return stem_geom(H, W, &g); });
+  m.def("stem_pack_input", [](at::Tensor x) {
+    check_cuda(x, "x");
+    TORCH_CHECK(x.scalar_type() == at::kBFloat16 && x.dim() == 4 && x.size(1) == 3 && x.is_contiguous(at::MemoryFormat::ChannelsLast),
+                "stem_pack_input: x must be bf16 [N,3,H,W] channels_last");
+    c10::cuda::CUDAGuard guard(x.device());
+    const int N = (int)x.size(0), H = (int)x.size(2), W = (int)x.size(3);
+    StemGeom g;
+    TORCH_CHECK(stem_geom(H, W, &g), "stem_pack_input: unsupported image size ", H, "x", W);
+    at::Tensor xp = at::empty({N, g.Hp2, g.Wp, 8}, x.options());
+    launch_stem_pack_input(x.data_ptr(), xp.data_ptr(), N, H, W, cur_stream());
+    return xp;
+  });
+  m.def("stem_pack_weight", [](at::Tensor w) {
+    check_cuda(w, "w");
+    TORCH_CHECK(w.scalar_type() == at::kBFloat16 && w.dim() == 4 && w.size(0) == 64 && w.size(1) == 3 && w.size(2) == 7 && w.size(3) == 7 &&
+                w.is_contiguous(at::MemoryFormat::ChannelsLast), "stem_pack_weight: w must be bf16 [64,3,7,7] channels_last");
+    c10::cuda::CUDAGuard guard(w.device());
+    at::Tensor w2 = at::empty({w.size(0), (int64_t)kStemK}, w.options().memory_format(at::MemoryFormat::Contiguous));
+    launch_stem_pack_weight(w.data_ptr(), w2.data_ptr(), (int)w.size(0), cur_stream());
+    return w2;
+  });
+  m.def("stem_conv_fprop_packed", [](at::Tensor xp, at::Tensor w2, int H, int W, bool stats, bool resident, bool debug) {
+    check_cuda(xp, "xp"); check_cuda(w2, "w2");
+    c10::cuda::CUDAGuard guard(xp.device());
+    StemGeom g;
+    const int N = (int)xp.size(0), K = (int)w2.size(0);
+    TORCH_CHECK(stem_geom(H, W, &g) && xp.dim() == 4 && xp.size(1) == g.Hp2 && xp.size(2) == g.Wp && xp.size(3) == 8 && xp.is_contiguous() &&
+                w2.dim() == 2 && w2.size(1) == kStemK && w2.is_contiguous() && xp.scalar_type() == at::kBFloat16 && w2.scalar_type() == at::kBFloat16,
+                "stem_conv_fprop_packed: operands do not match the packed layout");
+    at::Tensor y = at::empty({N, K, g.Ho, g.Wo}, xp.options().memory_format(at::MemoryFormat::ChannelsLast));
+    at::Tensor part, dbg;
+    float* sp = nullptr;
+    if (stats) { part = at::empty({2, stem_stat_groups(N, H, W), K}, xp.options().dtype(at::kFloat)); sp = part.data_ptr<float>(); }
+    if (debug) dbg = at::zeros({16}, xp.options().dtype(at::kLong));
+    launch_stem_conv_fprop(xp.data_ptr(), w2.data_ptr(), y.data_ptr(), N, H, W, K, sp, resident, debug ? dbg.data_ptr() : nullptr, cur_stream());
+    return std::make_tuple(y, part, dbg);
+  }, py::arg("xp"), py::arg("w2"), py::arg("H"), py::arg("W"), py::arg("stats") = false, py::arg("resident") = true, py::arg("debug") = false);
+  m.def("stem_conv_fprop", [](at::Tensor x, at::Tensor w, bool stats, bool resident) {
+    check_cuda(x, "x"); check_cuda(w, "w");
+    TORCH_CHECK(x.scalar_type() == at::kBFloat16 && w.scalar_type() == at::kBFloat16, "stem_conv_fprop: bf16 tensors");
+    TORCH_CHECK(x.dim() == 4 && x.size(1) == 3 && x.is_contiguous(at::MemoryFormat::ChannelsLast), "stem_conv_fprop: x must be [N,3,H,W] channels_last");
+    TORCH_CHECK(w.dim() == 4 && w.size(0) == 64 && w.size(1) == 3 && w.size(2) == 7 && w.size(3) == 7 && w.is_contiguous(at::MemoryFormat::ChannelsLast),
+                "stem_conv_fprop: w must be [64,3,7,7] channels_last");
+    c10::cuda::CUDAGuard guard(x.device());
+    const int N = (int)x.size(0), H = (int)x.size(2), W = (int)x.size(3), K = (int)w.size(0);
+    StemGeom g;
+    TORCH_CHECK(stem_geom(H, W, &g), "stem_conv_fprop: unsupported image size ", H, "x", W);
+    at::Tensor xp = at::empty({N, g.Hp2, g.Wp, 8}, x.options().memory_format(at::MemoryFormat::Contiguous));
+    at::Tensor w2 = at::empty({K, (int64_t)kStemK}, x.options().memory_format(at::MemoryFormat::Contiguous));
+    at::Tensor y = at::empty({N, K, g.Ho, g.Wo}, x.options().memory_format(at::MemoryFormat::ChannelsLast));
+    at::Tensor part;
+    float* sp = nullptr;
+    if (stats) { part = at::empty({2, stem_stat_groups(N, H, W), K}, x.options().dtype(at::kFloat).memory_format(at::MemoryFormat::Contiguous)); sp = part.data_ptr<float>(); }
+    cudaStream_t st = cur_stream();
+    launch_stem_pack_input(x.data_ptr(), xp.data_ptr(), N, H, W, st);
+    launch_stem_pack_weight(w.data_ptr(), w2.data_ptr(), K, st);
+    launch_stem_conv_fprop(xp.data_ptr(), w2.data_ptr(), y.data_ptr(), N, H, W, K, sp, resident, nullptr, st);
+    return std::make_tuple(y, part, xp);
+  }, py::arg("x"), py::arg("w"), py::arg("stats") = false, py::arg("resident") = true);
+  m.def("stem_conv_wgrad", [](at::Tensor dy, at::Tensor xp, int H, int W, int variant, bool unpack) {
+    check_cuda(dy, "dy"); check_cuda(xp, "xp");
+    TORCH_CHECK(dy.scalar_type() == at::kBFloat16 && xp.scalar_type() == at::kBFloat16, "stem_conv_wgrad: bf16 tensors");
+    TORCH_CHECK(dy.dim() == 4 && dy.is_contiguous(at::MemoryFormat::ChannelsLast) && xp.is_contiguous(), "stem_conv_wgrad: dy channels_last, xp packed");
+    TORCH_CHECK(variant == 0 || variant == 1, "stem_conv_wgrad: variant 0 (dedicated kernel) or 1 (generic kernel)");
+    c10::cuda::CUDAGuard guard(dy.device());
+    const int N = (int)dy.size(0), K = (int)dy.size(1);
+    StemGeom g;
+    TORCH_CHECK(stem_geom(H, W, &g) && dy.size(2) == g.Ho && dy.size(3) == g.Wo && xp.dim() == 4 && xp.size(0) == N && xp.size(1) == g.Hp2 &&
+                xp.size(2) == g.Wp && xp.size(3) == 8, "stem_conv_wgrad: geometry mismatch");
+    const size_t ws = stem_wgrad_workspace_floats(N, H, W, K, variant);
+    TORCH_CHECK(ws > 0, "stem_conv_wgrad: unsupported geometry");
+    auto plain = dy.options().memory_format(at::MemoryFormat::Contiguous);
+    at::Tensor work = at::empty({(int64_t)ws}, plain.dtype(at::kFloat));
+    at::Tensor dw2 = variant == 0 ? at::empty({(int64_t)kStemK, K}, plain) : at::empty({K, (int64_t)kStemK}, plain);
+    cudaStream_t st = cur_stream();
+    launch_stem_conv_wgrad(dy.data_ptr(), xp.data_ptr(), dw2.data_ptr(), N, H, W, K, variant, work.data_ptr<float>(), st);
+    if (!unpack) return dw2;
+    at::Tensor dw = at::empty({K, 3, 7, 7}, dy.options().memory_format(at::MemoryFormat::ChannelsLast));
+    launch_stem_unpack_wgrad(dw2.data_ptr(), dw.data_ptr(), K, variant == 0, st);
+    return dw;
+  }, py::arg("dy"), py::arg("xp"), py::arg("H"), py::arg("W"), py::arg("variant") = 0, py::arg("unpack") = true);
   m.def("conv_tile_plan", [](int N, int H, int W, int R, int S, int mode) {
     ConvTilePlan pl;
     const bool ok = conv_tile_plan(N, H, W, R, S, mode, &pl);

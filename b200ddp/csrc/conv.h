@@ -65,4 +65,35 @@ size_t conv_wgrad_workspace_floats(int N, int H, int W, int Cin, int Cout, int R
 void launch_conv_wgrad(const void* dy, const void* x, void* dw, int N, int H, int W, int Cin, int Cout, int R, int S,
                        const WgradCfg& cfg, float* workspace, cudaStream_t stream);
 
+
+// ---- the strided 7x7 stem (3 input channels, stride 2, padding 3) as a 4-tap implicit GEMM -------------------------------
+// The [N,H,W,3] input is repacked once per step into a zero-bordered image of ROW PAIRS, xp[N, H/2+3, W+8, 8]: "pixel"
+// (i, wp) holds padded rows 2i and 2i+1 (4 channels each, the 4th zero) of padded column wp; image pixel (h,w) sits at padded
+// (h+3, w+4).  A 16-byte pixel makes the 8-pixel window that starts at padded column 2*ow a 128-byte row whose start advances
+// by 32 bytes per output column - a legal TMA stride - so "im2col" is a tensor map with OVERLAPPING rows
+// {64 elements, Wo windows (stride 32 B), H/2+3 pair rows, N} and never exists in memory.  Output row oh reads pair rows
+// oh .. oh+3: four taps of 64 reduction elements each (K = 256 for 147 real filter taps; the rest meets zero weights).
+struct StemGeom { int Ho, Wo, Hp2, Wp; };
+inline bool stem_geom(int H, int W, StemGeom* g) {
+  if (H < 8 || W < 32 || H % 2 != 0 || W % 2 != 0) return false;
+  g->Ho = H / 2; g->Wo = W / 2; g->Hp2 = H / 2 + 3; g->Wp = W + 8;
+  return g->Wo <= 128 && g->Wo % 16 == 0;
+}
+constexpr int kStemTaps = 4;
+constexpr int kStemK = kStemTaps * 64;      // packed filter row: 4 pair rows x 8 window pixels x (2 rows x 4 channels)
+void launch_stem_pack_input(const void* x_nhwc3, void* xp, int N, int H, int W, cudaStream_t stream);
+void launch_stem_pack_weight(const void* w_krsc3, void* w2, int Cout, cudaStream_t stream);            // [Cout,7,7,3] -> [Cout,4,8,8]
+// packed weight gradient -> [Cout,7,7,3]; transposed: dw2 is [kStemK, Cout] (the dedicated kernel) instead of [Cout, kStemK]
+void launch_stem_unpack_wgrad(const void* dw2, void* dw_krsc3, int Cout, bool transposed, cudaStream_t stream);
+// y[N,Ho,Wo,Cout] = conv7x7s2(x) from the packed operands; col_stats optional [2][stem_stat_groups][Cout] (BatchNorm statistics).
+// resident_filter: the 32 KB packed filter is loaded into shared memory once per CTA instead of once per tile.
+int stem_stat_groups(int N, int H, int W);
+void launch_stem_conv_fprop(const void* xp, const void* w2, void* y, int N, int H, int W, int Cout, float* col_stats, bool resident_filter,
+                            void* debug_counters, cudaStream_t stream);
+// Weight gradient over the same windows.  variant 0: the dedicated kernel (window elements on the accumulator rows, two taps per
+// MMA, dw2 comes out transposed [kStemK, Cout]); variant 1: the generic split-pixel kernel with four taps (dw2 [Cout, kStemK]).
+size_t stem_wgrad_workspace_floats(int N, int H, int W, int Cout, int variant);
+void launch_stem_conv_wgrad(const void* dy, const void* xp, void* dw2, int N, int H, int W, int Cout, int variant, float* workspace,
+                            cudaStream_t stream);
+
 }  // namespace b200

@@ -60,6 +60,9 @@ struct TapGemmParams {
   uint32_t a_tx_bytes;
   int set_base_offset;
   int b_tap_stride;         // column distance between taps in the filter matrix (Cin of the filter tensor)
+  int row_mul;              // patch tiling: input row of output row h and tap r is row_mul * h + r - pad
+  int b_resident;           // flat / patch tilings with one n-tile: all filter chunks of a tile are loaded ONCE per CTA into ring B
+  int chunk_stride;         // bytes between consecutive k chunks of a ring-S stage (activation chunk [+ filter chunk])
   float* col_stats;         // [2][G][Nc] or nullptr (EPI 1: sum / sum of squares of the output; EPI 2: S1 / S2 of the BatchNorm backward)
   const __nv_bfloat16* addend;   // EPI 2: [M_total, Nc] added to the output (shortcut gradient) or nullptr
   const __nv_bfloat16* bn_x;     // EPI 2: [M_total, Nc] input of the BatchNorm whose backward consumes the output, or nullptr
@@ -152,7 +155,7 @@ conv_tap_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b); tma_prefetch_desc(&map_d); }
   if (warp == 1) {                                     // one lane per ring slot: the ~50 barrier inits are off the serial path
-    if (lane < kMaxRing) { mbar_init(&s_full[lane], p.mode == 2 ? 1 : 2); mbar_init(&s_empty[lane], 1); mbar_init(&b_full[lane], 1); mbar_init(&b_empty[lane], 1); }
+    if (lane < kMaxRing) { mbar_init(&s_full[lane], (p.mode == 2 || p.b_resident) ? 1 : 2); mbar_init(&s_empty[lane], 1); mbar_init(&b_full[lane], 1); mbar_init(&b_empty[lane], 1); }
     if (lane >= 16 && lane < 16 + kAccumStages) { mbar_init(&tmem_full[lane - 16], 1); mbar_init(&tmem_empty[lane - 16], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -176,12 +179,26 @@ conv_tap_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     uint32_t sph = 0, bph = 0;
     long long d_w = 0, d_i = 0, t = 0;
     const bool dbg = p.dbg != nullptr && blockIdx.x == 0;
+    if constexpr (!B_MN) {
+      if (!is_a && p.b_resident) {                         // the whole (small) filter of the single n-tile: once per CTA
+        if (elect_one()) {
+          mbar_expect_tx(&b_full[0], (uint32_t)chunks_per_tile * kBBytes);
+          int cb_i = 0, r_i = 0, s_i = 0;
+          for (int q = 0; q < chunks_per_tile; ++q) {
+            tma_load_2d(&map_b, &b_full[0], b_ring + q * kBBytes, (r_i * p.S + s_i) * p.b_tap_stride + cb_i * BLOCK_K, 0);
+            if (++s_i == p.S) { s_i = 0; if (++r_i == p.R) { r_i = 0; ++cb_i; } }
+          }
+        }
+        __syncwarp();
+      }
+    }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int mt = tile / p.num_n_tiles, nt = tile - mt * p.num_n_tiles;     // n-tiles of one patch run on neighbouring CTAs
       const int n0 = nt * BLOCK_N;
       int img0 = 0, h0 = 0;
       if (p.mode != 0) { img0 = (mt / p.tiles_h) * p.BI; h0 = (mt % p.tiles_h) * p.BH; }
       if (p.mode != 2) {
+        if (!is_a && p.b_resident) continue;               // nothing to stream for this warp
         int cb = 0, r = 0, sx = 0;                           // chunk q = (cb, tap (r, sx)), taps fastest
         for (int q0 = 0; q0 < chunks_per_tile; q0 += p.KC) {
           B200_T0 mbar_wait(&s_empty[ss], sph ^ 1); B200_T1(d_w)
@@ -196,9 +213,9 @@ conv_tap_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                   tma_load_4d(&map_a, &s_full[ss], dst, cb_i * BLOCK_K, mt * 128, 0, 0);
                 } else {
                   const int dh = p.mirror ? p.pad - r_i : r_i - p.pad, dw = p.mirror ? p.pad - s_i : s_i - p.pad;
-                  tma_load_4d(&map_a, &s_full[ss], dst, cb_i * BLOCK_K, dw, h0 + dh, img0);  // out-of-image rows / columns arrive as zeros
+                  tma_load_4d(&map_a, &s_full[ss], dst, cb_i * BLOCK_K, dw, h0 * p.row_mul + dh, img0);  // out-of-image rows / columns arrive as zeros
                 }
-                dst += p.a_chunk_bytes + kBBytes;
+                dst += p.chunk_stride;
                 if (++s_i == p.S) { s_i = 0; if (++r_i == p.R) { r_i = 0; ++cb_i; } }
               }
             } else {
@@ -213,7 +230,7 @@ conv_tap_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                   for (int c = 0; c < BLOCK_N / 64; ++c)                                      // box {64 n, 64 k} per chunk
                     tma_load_2d(&map_b, &s_full[ss], sb + c * (64 * BLOCK_K * 2), bcol + n0 + 64 * c, cb_i * BLOCK_K);
                 }
-                dst += p.a_chunk_bytes + kBBytes;
+                dst += p.chunk_stride;
                 if (++s_i == p.S) { s_i = 0; if (++r_i == p.R) { r_i = 0; ++cb_i; } }
               }
             }
@@ -275,6 +292,7 @@ conv_tap_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     uint32_t sph = 0, bph = 0, accum_phase = 0;
     long long d_wt = 0, d_wf = 0, d_mma = 0, d_cm = 0, t = 0;
     const bool dbg = p.dbg != nullptr && blockIdx.x == 0;
+    if (p.b_resident) { mbar_wait(&b_full[0], 0); tc_fence_after(); }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       B200_T0 mbar_wait(&tmem_empty[accum], accum_phase ^ 1); B200_T1(d_wt)
       tc_fence_after();
@@ -288,13 +306,14 @@ conv_tap_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             uint32_t off = (uint32_t)(ss * p.s_stage_bytes);
             for (int j = 0; j < p.KC; ++j) {
               const uint64_t da = a_desc0 + (uint64_t)(off >> 4);
-              const uint64_t db = b_desc_s0 + (uint64_t)((off + p.a_chunk_bytes) >> 4);
+              const uint64_t db = p.b_resident ? b_desc_b0 + (uint64_t)(((uint32_t)(q0 + j) * (uint32_t)kBBytes) >> 4)
+                                               : b_desc_s0 + (uint64_t)((off + p.a_chunk_bytes) >> 4);
 #pragma unroll
               for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                 umma_bf16(tmem_d, da + (uint64_t)(k * ((UMMA_K * 2) >> 4)), db + (uint64_t)(k * (kStepB >> 4)), idesc, acc);
                 acc = 1;
               }
-              off += (uint32_t)(p.a_chunk_bytes + kBBytes);
+              off += (uint32_t)p.chunk_stride;
             }
             umma_commit(&s_empty[ss]);
           }
@@ -654,19 +673,23 @@ void launch_variant(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensor
   const int taps = p.R * p.S;
   if (p.mode != 2) {
     // ring S stage = KC x (activation chunk + filter chunk): one barrier wait + one tcgen05.commit per KC * 4 MMAs
-    const int chunk = p.a_chunk_bytes + kBBytes;
     const int chunks_per_tile = (p.Kc / BLOCK_K) * taps;
+    if (p.b_resident && (B_MN || p.num_n_tiles != 1)) throw std::runtime_error("conv: a resident filter needs a K-major filter and one n-tile");
+    p.chunk_stride = p.a_chunk_bytes + (p.b_resident ? 0 : kBBytes);
+    p.b_slot_bytes = p.b_resident ? chunks_per_tile * kBBytes : 0;
+    p.b_stages = p.b_resident ? 1 : 0;
+    const int chunk = p.chunk_stride;
+    const int ring_budget = budget - p.b_stages * p.b_slot_bytes;
     int kc = want_kc > 0 ? want_kc : 2;
-    while (kc > 1 && (chunks_per_tile % kc != 0 || budget / (kc * chunk) < 3)) --kc;
+    while (kc > 1 && (chunks_per_tile % kc != 0 || ring_budget / (kc * chunk) < 3)) --kc;
     p.KC = kc; p.TB = 1;
     p.s_stage_bytes = kc * chunk;
-    p.s_stages = budget / p.s_stage_bytes;
+    p.s_stages = ring_budget / p.s_stage_bytes;
     if (p.s_stages > kMaxRing) p.s_stages = kMaxRing;
     if (p.s_stages < 2) throw std::runtime_error("conv: shared memory budget exceeded");
-    p.b_slot_bytes = 0; p.b_stages = 0;
   } else {
     // ring S = activation halo per channel block; ring B = TB filter taps per slot (a filter row when it fits)
-    p.KC = 1;
+    p.KC = 1; p.chunk_stride = 0; p.b_resident = 0;
     p.TB = (3 * kBBytes <= 48 * 1024 && taps % 3 == 0) ? 3 : 1;
     p.s_stage_bytes = p.a_chunk_bytes;
     p.b_slot_bytes = p.TB * kBBytes;
@@ -721,6 +744,8 @@ void launch_conv_tap_gemm(const void* a, const void* w, void* d, int N, int H, i
   if (p.a_chunk_bytes < 128 * 128) p.a_chunk_bytes = 128 * 128;   // the MMA reads 128 rows from the chunk start
   p.set_base_offset = cfg.set_base_offset;
   p.b_tap_stride = Cin;
+  p.row_mul = 1;
+  p.b_resident = 0;
   p.col_stats = col_stats;
   p.addend = fuse ? reinterpret_cast<const __nv_bfloat16*>(fuse->addend) : nullptr;
   p.bn_x = fuse ? reinterpret_cast<const __nv_bfloat16*>(fuse->bn_x) : nullptr;
@@ -773,6 +798,58 @@ void launch_conv_tap_gemm(const void* a, const void* w, void* d, int N, int H, i
   B200_CONV_DISPATCH(128)
   B200_CONV_DISPATCH(256)
 #undef B200_CONV_DISPATCH
+}
+
+// ---- strided 7x7 stem: the same kernel, patch tiling with one output row per tile and four taps of 64 over the row-pair image ----
+int stem_stat_groups(int N, int H, int W) {
+  StemGeom g;
+  if (!stem_geom(H, W, &g)) return 0;
+  return conv_grid_size(N * g.Ho, 1, true);
+}
+
+void launch_stem_conv_fprop(const void* xp, const void* w2, void* y, int N, int H, int W, int Cout, float* col_stats, bool resident_filter,
+                            void* debug_counters, cudaStream_t stream) {
+  StemGeom g;
+  if (!stem_geom(H, W, &g)) throw std::runtime_error("stem conv: unsupported image size");
+  if (Cout != 64) throw std::runtime_error("stem conv: 64 output channels");
+  const long long M_total = (long long)N * g.Ho * g.Wo;
+  TapGemmParams p{};
+  p.M_total = (int)M_total; p.Kc = 64; p.Nc = Cout;
+  p.R = kStemTaps; p.S = 1; p.pad = 0; p.mirror = 0;
+  p.mode = 1;
+  p.H = g.Ho; p.W = g.Wo; p.BH = 1; p.BI = 1; p.tiles_h = g.Ho; p.Wp = g.Wo;
+  p.num_m_tiles = N * g.Ho;
+  p.num_n_tiles = 1;
+  p.dense_rows = g.Wo;
+  p.a_tx_bytes = (uint32_t)(g.Wo * 128);
+  p.a_chunk_bytes = 128 * 128;
+  p.b_tap_stride = 64;
+  p.row_mul = 1;                                     // pair row of output row oh and tap t: oh + t
+  p.b_resident = resident_filter ? 1 : 0;
+  p.col_stats = col_stats;
+  p.dbg = reinterpret_cast<long long*>(debug_counters);
+  const uint64_t row_pitch = (uint64_t)g.Wp * 16;
+  CUtensorMap ma, mb, md;
+  {   // overlapping windows: 64 elements (8 sixteen-byte pixels) every 32 bytes
+    uint64_t dm[4] = {64, (uint64_t)g.Wo, (uint64_t)g.Hp2, (uint64_t)N};
+    uint64_t st[3] = {32, row_pitch, row_pitch * (uint64_t)g.Hp2};
+    uint32_t bx[4] = {64, (uint32_t)g.Wo, 1, 1};
+    ma = conv_encode_map(xp, 4, dm, st, bx);
+  }
+  {
+    uint64_t dm[2] = {(uint64_t)kStemK, (uint64_t)Cout};
+    uint64_t st[1] = {(uint64_t)kStemK * 2};
+    uint32_t bx[2] = {64, 64};
+    mb = conv_encode_map(w2, 2, dm, st, bx);
+  }
+  {
+    uint64_t dm[2] = {(uint64_t)Cout, (uint64_t)M_total};
+    uint64_t st[1] = {(uint64_t)Cout * 2};
+    uint32_t bx[2] = {64, (uint32_t)g.Wo};
+    md = conv_encode_map(y, 2, dm, st, bx);
+  }
+  if (col_stats != nullptr) launch_variant<64, false, 1>(ma, mb, md, p, 0, stream);
+  else launch_variant<64, false, 0>(ma, mb, md, p, 0, stream);
 }
 
 }  // namespace b200

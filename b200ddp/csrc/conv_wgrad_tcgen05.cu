@@ -34,6 +34,7 @@ struct WgradParams {
   int Cout, Cin, R, S, pad;
   int mode;                 // 0 flat (1x1): pixel block = KB consecutive pixels; 1 patch: pixel block = BI images x BH rows x W columns
   int H, W, BH, BI, tiles_h;
+  int row_mul;              // patch mode: x row of pixel-block row h and tap r is row_mul * h + r - pad (2 for the strided stem)
   int KB;                   // pixels (shared-memory rows) per pixel block, multiple of 16
   int num_kblocks;          // pixel blocks in the whole tensor
   int MB, TG, tile_n;       // Cout blocks of 128 per CTA, taps per CTA, input channels per CTA
@@ -136,7 +137,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
           mbar_expect_tx(&b_full[bs], (uint32_t)(b_chunks * chunk_bytes));
           for (int j = 0; j < b_chunks; ++j)
             tma_load_4d(&map_x, &b_full[bs], b_ring + bs * p.b_slot_bytes + j * chunk_bytes, ci0 + 64 * j,
-                        p.mode == 0 ? c1 : sx - p.pad, p.mode == 0 ? 0 : c2 + r - p.pad, c3);
+                        p.mode == 0 ? c1 : sx - p.pad, p.mode == 0 ? 0 : c2 * p.row_mul + r - p.pad, c3);
         }
         __syncwarp();
         if (++sx == p.S) { sx = 0; ++r; }
@@ -256,7 +257,7 @@ bool wgrad_plan(int N, int H, int W, int Cin, int Cout, int R, int S, const Wgra
   if (Cin % 64 != 0 || Cout % 64 != 0 || R != S || (R != 1 && R != 3)) return false;
   WgradParams p{};
   p.Cout = Cout; p.Cin = Cin; p.R = R; p.S = S; p.pad = (R - 1) / 2;
-  p.H = H; p.W = W;
+  p.H = H; p.W = W; p.row_mul = 1;
   const int taps = R * S;
   if (taps == 1) {
     p.mode = 0; p.KB = 64;
@@ -367,6 +368,259 @@ void launch_conv_wgrad(const void* dy, const void* x, void* dw, int N, int H, in
   B200_CUDA_CHECK(cudaGetLastError());
   const size_t n = (size_t)Cout * R * S * Cin;
   conv_wgrad_reduce_kernel<<<(unsigned)((n / 8 + 31) / 32), 256, 0, stream>>>(workspace, reinterpret_cast<__nv_bfloat16*>(dw), n, p.split);
+  B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(2);
+}
+
+// ---- strided 7x7 stem (conv.h): the x operand is the overlapping-window tensor map over the row-pair image --------------------
+// Dedicated kernel (variant 0).  The generic kernel above puts Cout on the accumulator rows, which for Cout = 64 wastes half of
+// every MMA and needs one MMA group per tap.  Here the WINDOW ELEMENTS are the rows: one 128-row operand = two taps side by side
+// (two 64-wide MN-major chunks, LBO apart), the 64 output channels are the columns:
+//   D_g[(tap 2g + c) * 64 + e, co] += sum over the pixels of one output row of  window_{2g+c}[pixel, e] * dy[pixel, co],   g = 0, 1
+// -> two MMA groups per output row instead of four (seven before the row-pair packing), every dy row loaded once and never
+// zero-padded.  Pixel range split over all SMs, fp32 partials [split][256][Cout], reduced by conv_wgrad_reduce_kernel.
+namespace {
+
+struct StemWgradParams {
+  int KB;                   // pixels per block = Wo
+  int Ho, num_kblocks, split, Cout;
+  int chunk_bytes, a_stages, b_stages;
+  float* partial;           // [split][kStemK][Cout]
+};
+constexpr int kStemGroups = kStemTaps / 2;
+
+__global__ void __launch_bounds__(kThreads, 1)
+stem_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy, const StemWgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int a_slot_bytes = 2 * p.chunk_bytes;
+  uint8_t* a_ring = smem;                                    // window pairs
+  uint8_t* b_ring = a_ring + p.a_stages * a_slot_bytes;      // dy rows
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(b_ring + p.b_stages * p.chunk_bytes);
+  uint64_t* a_empty = a_full + kMaxRing;
+  uint64_t* b_full = a_empty + kMaxRing;
+  uint64_t* b_empty = b_full + kMaxRing;
+  uint64_t* acc_full = b_empty + kMaxRing;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  constexpr uint32_t kTmemCols = 128;                        // two accumulators of 64 columns
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sp = blockIdx.x;
+  const int kb0 = (int)(((long long)p.num_kblocks * sp) / p.split);
+  const int kb1 = (int)(((long long)p.num_kblocks * (sp + 1)) / p.split);
+
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_dy); }
+  if (warp == 1) {
+    if (lane < kMaxRing) { mbar_init(&a_full[lane], 1); mbar_init(&a_empty[lane], 1); mbar_init(&b_full[lane], 1); mbar_init(&b_empty[lane], 1); }
+    if (lane == 16) mbar_init(acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== window producer: two taps (pair rows oh + 2g, oh + 2g + 1) per slot =====================
+    int as = 0;
+    uint32_t aph = 0;
+    for (int kb = kb0; kb < kb1; ++kb) {
+      const int img = kb / p.Ho, oh = kb - img * p.Ho;
+      for (int g = 0; g < kStemGroups; ++g) {
+        mbar_wait(&a_empty[as], aph ^ 1);
+        if (elect_one()) {
+          uint8_t* dst = a_ring + as * a_slot_bytes;
+          mbar_expect_tx(&a_full[as], (uint32_t)(2 * p.chunk_bytes));
+          tma_load_4d(&map_x, &a_full[as], dst, 0, 0, oh + 2 * g, img);
+          tma_load_4d(&map_x, &a_full[as], dst + p.chunk_bytes, 0, 0, oh + 2 * g + 1, img);
+        }
+        __syncwarp();
+        if (++as == p.a_stages) { as = 0; aph ^= 1; }
+      }
+    }
+  } else if (warp == 3) {
+    // ===================== dy producer: one output row of gradients per slot =====================
+    int bs = 0;
+    uint32_t bph = 0;
+    for (int kb = kb0; kb < kb1; ++kb) {
+      const int img = kb / p.Ho, oh = kb - img * p.Ho;
+      mbar_wait(&b_empty[bs], bph ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(&b_full[bs], (uint32_t)p.chunk_bytes);
+        tma_load_4d(&map_dy, &b_full[bs], b_ring + bs * p.chunk_bytes, 0, 0, oh, img);
+      }
+      __syncwarp();
+      if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = idesc_mn(64);
+    const int ksteps = p.KB / UMMA_K;
+    const uint64_t a_desc0 = make_smem_desc(smem_u32(a_ring), (uint32_t)p.chunk_bytes, 1024);
+    const uint64_t b_desc0 = make_smem_desc(smem_u32(b_ring), (uint32_t)p.chunk_bytes, 1024);
+    int as = 0, bs = 0;
+    uint32_t aph = 0, bph = 0;
+    for (int kb = kb0; kb < kb1; ++kb) {
+      mbar_wait(&b_full[bs], bph);
+      for (int g = 0; g < kStemGroups; ++g) {
+        mbar_wait(&a_full[as], aph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t da0 = a_desc0 + (uint64_t)((uint32_t)(as * a_slot_bytes) >> 4);
+          const uint64_t db0 = b_desc0 + (uint64_t)((uint32_t)(bs * p.chunk_bytes) >> 4);
+          for (int k = 0; k < ksteps; ++k)
+            umma_bf16(tmem_base + (uint32_t)(g * 64), da0 + (uint64_t)(k * ((UMMA_K * 128) >> 4)), db0 + (uint64_t)(k * ((UMMA_K * 128) >> 4)), idesc,
+                      (kb != kb0 || k != 0) ? 1u : 0u);
+          umma_commit(&a_empty[as]);
+          if (g == kStemGroups - 1) umma_commit(&b_empty[bs]);
+        }
+        __syncwarp();
+        if (++as == p.a_stages) { as = 0; aph ^= 1; }
+      }
+      if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
+    }
+    if (elect_one()) umma_commit(acc_full);
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===================== epilogue: TMEM -> fp32 partial [kStemK][Cout] of this split =====================
+    const int ew = warp - 4;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    float* base = p.partial + (size_t)sp * kStemK * p.Cout;
+    for (int g = 0; g < kStemGroups; ++g) {
+      const int row = g * 128 + ew * 32 + lane;              // packed filter index k
+      float* out = base + (size_t)row * p.Cout;
+#pragma unroll 1
+      for (int c = 0; c < 64; c += 32) {
+        uint32_t rr[32];
+        tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(g * 64 + c), rr);
+        tmem_ld_wait();
+        if (kb1 > kb0) {
+#pragma unroll
+          for (int q = 0; q < 32; q += 4)
+            *reinterpret_cast<float4*>(out + c + q) = make_float4(__uint_as_float(rr[q]), __uint_as_float(rr[q + 1]), __uint_as_float(rr[q + 2]), __uint_as_float(rr[q + 3]));
+        } else {
+#pragma unroll
+          for (int q = 0; q < 32; q += 4) *reinterpret_cast<float4*>(out + c + q) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+bool stem_generic_plan(int N, int H, int W, int Cout, WgradPlan* out) {      // variant 1: generic kernel, four taps
+  StemGeom g;
+  if (!stem_geom(H, W, &g) || Cout != 64) return false;
+  WgradParams p{};
+  p.Cout = Cout; p.Cin = 64; p.R = kStemTaps; p.S = 1; p.pad = 0;
+  p.mode = 1; p.H = g.Ho; p.W = g.Wo; p.BH = 1; p.BI = 1; p.tiles_h = g.Ho; p.row_mul = 1;
+  p.KB = g.Wo;
+  p.num_kblocks = N * g.Ho;
+  p.MB = 1; p.TG = kStemTaps; p.tile_n = 64;
+  p.m_groups = 1; p.n_tiles = 1; p.tap_groups = 1;
+  p.split = p.num_kblocks < kNumSMs ? p.num_kblocks : kNumSMs;
+  p.tmem_cols = 256;
+  const int chunk = p.KB * 128;
+  p.a_slot_bytes = 2 * chunk;
+  p.b_slot_bytes = chunk;
+  const int budget = 227 * 1024 - kBarrierBytes - 1024;
+  p.a_stages = 3;
+  int bst = (budget - p.a_stages * p.a_slot_bytes) / p.b_slot_bytes;
+  if (bst > kMaxRing) bst = kMaxRing;
+  if (bst < 2) return false;
+  p.b_stages = bst;
+  out->p = p;
+  out->smem = p.a_stages * p.a_slot_bytes + p.b_stages * p.b_slot_bytes + kBarrierBytes + 1024;
+  out->grid = p.split;
+  return true;
+}
+
+bool stem_dedicated_plan(int N, int H, int W, int Cout, StemWgradParams* out, int* smem) {
+  StemGeom g;
+  if (!stem_geom(H, W, &g) || Cout != 64) return false;
+  StemWgradParams p{};
+  p.KB = g.Wo; p.Ho = g.Ho; p.Cout = Cout;
+  p.num_kblocks = N * g.Ho;
+  p.split = p.num_kblocks < kNumSMs ? p.num_kblocks : kNumSMs;
+  p.chunk_bytes = p.KB * 128;
+  const int budget = 227 * 1024 - kBarrierBytes - 1024;
+  p.b_stages = 3;
+  int ast = (budget - p.b_stages * p.chunk_bytes) / (2 * p.chunk_bytes);
+  if (ast > kMaxRing) ast = kMaxRing;
+  if (ast < 2) return false;
+  p.a_stages = ast;
+  *out = p;
+  *smem = p.a_stages * 2 * p.chunk_bytes + p.b_stages * p.chunk_bytes + kBarrierBytes + 1024;
+  return true;
+}
+}  // namespace
+
+size_t stem_wgrad_workspace_floats(int N, int H, int W, int Cout, int variant) {
+  if (variant == 1) {
+    WgradPlan pl;
+    if (!stem_generic_plan(N, H, W, Cout, &pl)) return 0;
+    return (size_t)pl.p.split * Cout * kStemK;
+  }
+  StemWgradParams p; int smem;
+  if (!stem_dedicated_plan(N, H, W, Cout, &p, &smem)) return 0;
+  return (size_t)p.split * Cout * kStemK;
+}
+
+void launch_stem_conv_wgrad(const void* dy, const void* xp, void* dw2, int N, int H, int W, int Cout, int variant, float* workspace,
+                            cudaStream_t stream) {
+  StemGeom g;
+  if (!stem_geom(H, W, &g)) throw std::runtime_error("stem wgrad: unsupported geometry");
+  CUtensorMap mdy, mx;
+  uint32_t bx[4] = {64, (uint32_t)g.Wo, 1, 1};
+  {
+    uint64_t dd[4] = {(uint64_t)Cout, (uint64_t)g.Wo, (uint64_t)g.Ho, (uint64_t)N};
+    uint64_t ds[3] = {(uint64_t)Cout * 2, (uint64_t)g.Wo * Cout * 2, (uint64_t)g.Ho * g.Wo * Cout * 2};
+    mdy = conv_encode_map(dy, 4, dd, ds, bx);
+  }
+  {
+    const uint64_t row_pitch = (uint64_t)g.Wp * 16;
+    uint64_t xd[4] = {64, (uint64_t)g.Wo, (uint64_t)g.Hp2, (uint64_t)N};
+    uint64_t xs[3] = {32, row_pitch, row_pitch * (uint64_t)g.Hp2};
+    mx = conv_encode_map(xp, 4, xd, xs, bx);
+  }
+  const size_t n = (size_t)Cout * kStemK;
+  int split = 0;
+  if (variant == 1) {
+    WgradPlan pl;
+    if (!stem_generic_plan(N, H, W, Cout, &pl)) throw std::runtime_error("stem wgrad: unsupported geometry");
+    WgradParams p = pl.p;
+    p.partial = workspace;
+    static bool configured = false;
+    if (!configured) {
+      B200_CUDA_CHECK(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      configured = true;
+    }
+    conv_wgrad_kernel<<<pl.grid, kThreads, pl.smem, stream>>>(mdy, mx, p);
+    split = p.split;
+  } else {
+    StemWgradParams p; int smem;
+    if (!stem_dedicated_plan(N, H, W, Cout, &p, &smem)) throw std::runtime_error("stem wgrad: unsupported geometry");
+    p.partial = workspace;
+    static bool configured = false;
+    if (!configured) {
+      B200_CUDA_CHECK(cudaFuncSetAttribute(stem_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      configured = true;
+    }
+    stem_wgrad_kernel<<<p.split, kThreads, smem, stream>>>(mx, mdy, p);
+    split = p.split;
+  }
+  B200_CUDA_CHECK(cudaGetLastError());
+  conv_wgrad_reduce_kernel<<<(unsigned)((n / 8 + 31) / 32), 256, 0, stream>>>(workspace, reinterpret_cast<__nv_bfloat16*>(dw2), n, split);
   B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(2);
 }
 

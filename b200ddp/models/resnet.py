@@ -1,7 +1,7 @@
 """ResNet-50 / ResNet-152 (He et al.) for the BASELINE.json perf configs.  Own definition (not
 torchvision's module) so that the stride-1 1x1 / 3x3 convolutions, BatchNorm(+add+ReLU), the stem pool and the classifier
 run on this package's kernels; parameter order / shapes match torchvision's - bucket layouts quoted in SURVEY §2.4-K4
-therefore hold.  The 7x7 stem and the six stride-2 convolutions stay on the library."""
+therefore hold.  The 7x7 stem runs on the tcgen05 tap-GEMM (``ops.StemConv7x7``); the six stride-2 convolutions stay on the library."""
 from __future__ import annotations
 
 import os
@@ -10,7 +10,7 @@ from typing import List
 import torch
 import torch.nn as nn
 
-from ..ops import Conv3x3, FusedBatchNormAct2d, Linear, MaxPool3x3s2, PointwiseConv2d
+from ..ops import Conv3x3, FusedBatchNormAct2d, Linear, MaxPool3x3s2, PointwiseConv2d, StemConv7x7
 from ..ops.bottleneck import bottleneck_forward, bottleneck_native_ok
 
 
@@ -49,7 +49,7 @@ class ResNet(nn.Module):
     def __init__(self, layers: List[int], num_classes: int = 1000, zero_init_residual: bool = False):
         super().__init__()
         self.inplanes = 64
-        self.conv1 = nn.Conv2d(3, 64, 7, stride=2, padding=3, bias=False)
+        self.conv1 = StemConv7x7(3, 64)
         self.bn1 = FusedBatchNormAct2d(64, relu=True)
         self.maxpool = MaxPool3x3s2()
         self.layer1 = self._make_layer(64, layers[0], 1)
@@ -80,7 +80,8 @@ class ResNet(nn.Module):
         return nn.Sequential(*mods)
 
     def forward(self, x):
-        x = self.maxpool(self.bn1(self.conv1(x)))
+        y, part = self.conv1.forward_with_stats(x)           # BatchNorm statistics ride on the stem's epilogue
+        x = self.maxpool(self.bn1(y, partials=part))
         x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
         x = torch.flatten(self.avgpool(x), 1)
         return self.fc(x)

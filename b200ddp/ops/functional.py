@@ -240,6 +240,63 @@ def conv2d_tc(x: torch.Tensor, weight: torch.Tensor, want_stats: bool = False):
 
 
 # ------------------------------------------------------------------------------------------------
+# The strided 7x7 stem (reference hot path: the model's first convolution, /root/reference/ddp.py:221,231)
+# ------------------------------------------------------------------------------------------------
+def _stem_policy() -> str:
+    """B200DDP_STEM: ``native`` (default) = the tcgen05 stem kernels where they apply, ``lib`` = library."""
+    return os.environ.get("B200DDP_STEM", "native")
+
+
+def stem_conv_supported(x: torch.Tensor, weight: torch.Tensor, stride, padding) -> bool:
+    """[N,3,H,W] channels_last bf16 CUDA input that needs no gradient, [64,3,7,7] channels_last bf16 filter, stride 2,
+    padding 3, even H / W with W / 2 a multiple of 16 and <= 128 (one output row per accumulator tile)."""
+    if _stem_policy() == "lib" or not (x.is_cuda and x.dim() == 4 and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16):
+        return False
+    if tuple(weight.shape) != (64, 3, 7, 7) or tuple(stride) != (2, 2) or tuple(padding) != (3, 3) or x.shape[1] != 3:
+        return False
+    if x.requires_grad and torch.is_grad_enabled():
+        return False                                     # no data-gradient kernel: the first layer's input is data
+    if not (x.is_contiguous(memory_format=torch.channels_last) and weight.is_contiguous(memory_format=torch.channels_last)):
+        return False
+    return bool(_C().stem_conv_supported(int(x.shape[2]), int(x.shape[3])))
+
+
+class _StemConv(torch.autograd.Function):
+    """y = conv7x7/s2(x, w) on the tcgen05 tap-GEMM: the input is repacked into a zero-bordered image of row pairs whose
+    overlapping 128-byte windows ARE the im2col rows (one TMA tensor map, nothing materialised; csrc/conv.h); optional
+    BatchNorm-statistics epilogue.  Backward: weight gradient over the same windows on the dedicated split-pixel tcgen05
+    kernel (``B200DDP_STEM_WGRAD=generic`` selects the general kernel); the input gets no gradient."""
+
+    @staticmethod
+    def forward(ctx, x, w, want_stats):
+        resident = os.environ.get("B200DDP_STEM_RESIDENT", "1") != "0"
+        y, st, xp = _C().stem_conv_fprop(x, w, bool(want_stats), resident)
+        ctx.save_for_backward(xp)
+        ctx.hw = (int(x.shape[2]), int(x.shape[3]))
+        ctx.w_strides = w.stride()
+        if want_stats:
+            ctx.mark_non_differentiable(st)
+            return y, st
+        return y, None
+
+    @staticmethod
+    def backward(ctx, dy, _dstats):
+        (xp,) = ctx.saved_tensors
+        dw = None
+        if ctx.needs_input_grad[1]:
+            variant = 1 if os.environ.get("B200DDP_STEM_WGRAD", "dedicated") == "generic" else 0
+            dw = _C().stem_conv_wgrad(_cl(dy), xp, ctx.hw[0], ctx.hw[1], variant)
+            if tuple(dw.stride()) != tuple(ctx.w_strides):
+                dw = dw.as_strided(dw.shape, ctx.w_strides)
+        return None, dw, None
+
+
+def stem_conv(x: torch.Tensor, weight: torch.Tensor, want_stats: bool = False):
+    """(y, partial BatchNorm statistics or None).  Caller checks ``stem_conv_supported`` first."""
+    return _StemConv.apply(x, weight, want_stats)
+
+
+# ------------------------------------------------------------------------------------------------
 # Losses: forward computes loss AND input gradient in one launch
 # ------------------------------------------------------------------------------------------------
 class _MSEFused(torch.autograd.Function):

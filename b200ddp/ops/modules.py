@@ -71,6 +71,28 @@ class Conv3x3(Conv2dTC):
         super().__init__(in_channels, out_channels, 3, stride=stride, **kw)
 
 
+class StemConv7x7(nn.Conv2d):
+    """The ResNet stem: bias-free ``nn.Conv2d(3, 64, 7, stride=2, padding=3)`` (same parameter name / shape / init) that runs
+    forward and weight gradient on the tcgen05 kernels for channels_last bf16 CUDA input, and hands the following BatchNorm
+    its statistics from the epilogue; anything else takes the stock path."""
+
+    def __init__(self, in_channels: int = 3, out_channels: int = 64, **kw):
+        super().__init__(in_channels, out_channels, 7, stride=2, padding=3, bias=False, **kw)
+
+    def _native(self, x: torch.Tensor) -> bool:
+        return Fn.stem_conv_supported(x, self.weight, self.stride, self.padding)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self._native(x):
+            return Fn.stem_conv(x, self.weight, False)[0]
+        return super().forward(x)
+
+    def forward_with_stats(self, x: torch.Tensor):
+        if self._native(x):
+            return Fn.stem_conv(x, self.weight, True)
+        return super().forward(x), None
+
+
 class LayerNorm(nn.Module):
     def __init__(self, hidden: int, eps: float = 1e-5, device=None, dtype=None):
         super().__init__()

@@ -128,3 +128,45 @@ def test_conv_module_falls_back_on_cpu_and_keeps_parameter_layout():
     assert torch.allclose(m(x), ref(x))
     y, part = PointwiseConv2d(8, 4, stride=2).forward_with_stats(x)
     assert part is None and y.shape == (2, 4, 3, 3)
+
+
+def test_stem_window_algebra_and_geometry():
+    """The layout contract of the tcgen05 stem (csrc/conv.h): with the input repacked into a zero-bordered image of ROW PAIRS
+    (16-byte pixels: padded rows 2i and 2i+1, 4 channels each), the 64-element window starting every 16 elements (32 bytes)
+    of pair row oh + t IS the im2col row of filter rows 2t, 2t+1 - for forward and weight gradient.  Checked here in plain
+    PyTorch against F.conv2d; the host-side geometry predicate too."""
+    import torch
+    import torch.nn.functional as F
+    from b200ddp import _ext
+    C = _ext.get()
+    assert C.stem_conv_supported(224, 224) and C.stem_conv_supported(64, 96)
+    assert not C.stem_conv_supported(224, 225) and not C.stem_conv_supported(224, 512) and not C.stem_conv_supported(224, 40)
+    torch.manual_seed(0)
+    n, h, w, k = 2, 32, 64, 64
+    x, wt = torch.randn(n, 3, h, w), torch.randn(k, 3, 7, 7)
+    ho, wo, hp2, wp = h // 2, w // 2, h // 2 + 3, w + 8
+    pad = torch.zeros(n, 2 * hp2, wp, 4)                       # padded image: pixel (h, w) at (h + 3, w + 4), 4th channel zero
+    pad[:, 3:3 + h, 4:4 + w, :3] = x.permute(0, 2, 3, 1)
+    xp = torch.cat([pad[:, 0::2], pad[:, 1::2]], dim=3)         # [n, hp2, wp, 8]: rows 2i | 2i+1
+    w2 = torch.zeros(k, 4, 8, 8)                                # [co, t, p, j]: r = 2t + j // 4, s = p - 1, c = j % 4
+    wr = torch.zeros(k, 8, 7, 4)
+    wr[:, :7, :, :3] = wt.permute(0, 2, 3, 1)
+    for t in range(4):
+        for half in range(2):
+            w2[:, t, 1:8, 4 * half:4 * half + 4] = wr[:, 2 * t + half]
+    w2 = w2.reshape(k, 256)
+    flat = xp.reshape(n, hp2, wp * 8)
+    dy = torch.randn(n, ho, wo, k)
+    y = torch.zeros(n, ho, wo, k)
+    dw2 = torch.zeros(k, 4, 64)
+    for t in range(4):
+        win = flat[:, t:t + ho, :].unfold(2, 64, 16)[:, :, :wo, :]
+        y += win @ w2[:, t * 64:(t + 1) * 64].t()
+        dw2[:, t, :] = torch.einsum("nhwk,nhwe->ke", dy, win)
+    wg = wt.clone().requires_grad_(True)
+    ref = F.conv2d(x, wg, None, 2, 3)
+    ref.backward(dy.permute(0, 3, 1, 2))
+    assert torch.allclose(y, ref.detach().permute(0, 2, 3, 1), atol=1e-3)
+    d = dw2.reshape(k, 4, 8, 2, 4)                               # [co, t, p, half, c]
+    dw = torch.stack([d[:, r // 2, 1:8, r % 2, :3] for r in range(7)], dim=1).permute(0, 3, 1, 2)   # [co, c, r, s]
+    assert torch.allclose(dw, wg.grad, atol=2e-3, rtol=1e-4)

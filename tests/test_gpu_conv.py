@@ -178,3 +178,62 @@ def test_fused_bottleneck_node_equals_the_per_layer_composition(with_downsample,
         assert p.grad.stride() == p.stride(), n
     for (n, u), v in zip(a.named_buffers(), b.buffers()):
         assert torch.allclose(u.float(), v.float(), atol=1e-3), n
+
+
+# ---- the strided 7x7 stem ------------------------------------------------------------------------------------------
+STEM_SHAPES = [(2, 224, 224), (3, 64, 96), (1, 32, 256), (32, 224, 224)]   # n, h, w   (w / 2 a multiple of 16, <= 128)
+
+
+def _stem_mk(n, h, w):
+    torch.manual_seed(n + h + w)
+    x = torch.randn(n, 3, h, w, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    wt = (torch.randn(64, 3, 7, 7, device="cuda") / 147 ** 0.5).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    dy = torch.randn(n, 64, h // 2, w // 2, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    return x, wt, dy
+
+
+@pytest.mark.parametrize("n,h,w", STEM_SHAPES)
+def test_stem_forward_statistics_and_weight_gradient_match_fp32_reference(n, h, w):
+    from b200ddp import _ext
+    C = _ext.get()
+    x, wt, dy = _stem_mk(n, h, w)
+    wf = wt.float().requires_grad_(True)
+    y_ref = F.conv2d(x.float(), wf, None, 2, 3)
+    y_ref.backward(dy.float())
+    for stats in (False, True):
+        for resident in (True, False):
+            y, part, xp = C.stem_conv_fprop(x, wt, stats, resident)
+            assert y.shape == y_ref.shape and y.is_contiguous(memory_format=torch.channels_last)
+            assert _rel(y, y_ref) < 6e-3, (stats, resident, _rel(y, y_ref))
+            if stats:
+                s = part.sum(dim=1)
+                yf = y.float()
+                assert torch.allclose(s[0], yf.sum(dim=(0, 2, 3)), rtol=2e-3, atol=2e-2 * (n * h * w) ** 0.5)
+                assert torch.allclose(s[1], (yf * yf).sum(dim=(0, 2, 3)), rtol=2e-3, atol=1e-2)
+    for variant in (0, 1):                                   # dedicated kernel / generic split-pixel kernel
+        dw = C.stem_conv_wgrad(dy, xp, h, w, variant)
+        assert dw.shape == wt.shape and dw.is_contiguous(memory_format=torch.channels_last)
+        assert _rel(dw, wf.grad) < 6e-3, (variant, _rel(dw, wf.grad))
+
+
+def test_stem_module_matches_stock_conv_through_autograd():
+    """ops.StemConv7x7 (native path) against nn.Conv2d with the same weights: output, weight gradient, and the BatchNorm that
+    consumes the epilogue statistics against the same BatchNorm computing its own."""
+    import torch.nn as nn
+    from b200ddp.ops import FusedBatchNormAct2d, StemConv7x7
+    x, wt, dy = _stem_mk(4, 224, 224)
+    ours = StemConv7x7().cuda().to(torch.bfloat16).to(memory_format=torch.channels_last)
+    stock = nn.Conv2d(3, 64, 7, 2, 3, bias=False).cuda().to(torch.bfloat16).to(memory_format=torch.channels_last)
+    with torch.no_grad():
+        ours.weight.copy_(wt); stock.weight.copy_(wt)
+    assert ours._native(x)
+    bn_a, bn_b = FusedBatchNormAct2d(64, relu=True).cuda(), FusedBatchNormAct2d(64, relu=True).cuda()
+    y, part = ours.forward_with_stats(x)
+    za = bn_a(y, partials=part)
+    zb = bn_b(stock(x))
+    assert part is not None and _rel(za, zb) < 1e-2, _rel(za, zb)
+    assert torch.allclose(bn_a.running_mean, bn_b.running_mean, atol=2e-3) and torch.allclose(bn_a.running_var, bn_b.running_var, rtol=1e-2, atol=1e-3)
+    za.backward(dy)
+    zb.backward(dy)
+    assert ours.weight.grad.stride() == ours.weight.stride()
+    assert _rel(ours.weight.grad, stock.weight.grad) < 2e-2, _rel(ours.weight.grad, stock.weight.grad)
