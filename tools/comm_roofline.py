@@ -16,25 +16,24 @@ LINK_GBS = 770.0          # measured peer copy per direction (B200_PROFILING.md)
 
 
 # Measured step times with and without the gradient exchange (same binary, `bench.py --no_comm` disables the hooks);
-# sources: profiles/ddp_overhead_diag_n2_v3.txt, profiles/scale_n4_v1.txt, profiles/bench_r1_n8_ours.json.
+# sources: profiles/ddp_overhead_r2.txt, profiles/bench_r2_n8_ours{,_nocomm}.json, profiles/ddp_timeline_r2.md.
 DDP_SECTION = """
-## The fused gradient path inside the ResNet-50 step
+## The fused gradient path inside the ResNet-50 step (round 2)
 
 Wire bytes per step: 51.2 MB (25.6 M gradients; bf16 convolution / linear gradients stay bf16 on the wire, fp32 BatchNorm
-gradients stay fp32), in 5 buckets launched in completion order on a high-priority stream while backward is still running.
+gradients stay fp32), in 5 buckets launched in completion order on a forked high-priority stream while backward is still running.
 Link-roofline time = 2(W-1)/W x 51.2 MB / 770 GB/s.  What the step actually pays is the *exposed* part: step time with the
 exchange minus step time with `--no_comm`.
 
-| GPUs | step, exchange on | step, exchange off | exposed | link-roofline time of the exchange | exposed / step |
-|---|---|---|---|---|---|
-| 2 | 8.737 ms | 8.230 ms | 0.507 ms | 0.066 ms | 5.8 % |
-| 4 | 5.366 ms | 4.992 ms | 0.374 ms | 0.100 ms | 7.0 % |
-| 8 | 5.455 ms | 5.0 ms (1-GPU step; no 8-GPU `--no_comm` run) | ~0.46 ms | 0.116 ms | 8.3 % |
+| GPUs | step, exchange on | step, exchange off | exposed | link-roofline time of the exchange | exposed / step | round 1 |
+|---|---|---|---|---|---|---|
+| 2 | 5.157-5.186 ms | 4.956-4.960 ms | 0.20-0.23 ms | 0.066 ms | 4.2 % | 5.30-5.35 ms, 0.34-0.39 ms exposed |
+| 8 | 5.229 ms | 4.985 ms | 0.244 ms | 0.116 ms | 4.7 % | 5.456 ms |
 
-(The 2-GPU row predates the fused BatchNorm work, hence the longer step.)  The exposed part is 3.7-7.7x the link time of the
-whole exchange: the buckets that overlap are free, the residue is the last bucket (launch after the final gradient, two
-peer rendezvous, 3 MiB on the wire) plus SM time the light comm CTAs take from backward.  `docs/ROADMAP.md` section 4 lists
-what is left to try; block-count sweeps (ov8 / ov24 / ov48, tail 24 / 96 in `ddp_overhead_diag_n2_v3.txt`) move it by < 1 %.
+`ddp_timeline_r2.md` attributes the 0.20-0.23 ms at 2 GPUs: ~110 us of backward kernels running slower while the 24
+communication CTAs are resident, 37-45 us for the last bucket (now a single-rendezvous NVLS one-shot kernel) after the last
+gradient, <= 35 us for the BatchNorm-buffer broadcast at the start of backward; the ~170 us of round 1 that was neither of
+these was a CUDA-graph replay effect triggered by the eager warm-up (`graph_replay_modes.md`) and is gone.
 """
 
 
@@ -70,7 +69,7 @@ def table(path: Path) -> str:
 
 def main() -> None:
     root = Path(__file__).resolve().parent.parent / "profiles"
-    files = [Path(a) for a in sys.argv[1:]] or sorted(root.glob("sweep_n*_v*.json"))
+    files = [Path(a) for a in sys.argv[1:]] or sorted(root.glob("sweep_n*_*.json"))
     latest = {}
     for f in files:                                   # keep the newest version per world size
         w = json.loads(f.read_text())["world"]
@@ -80,8 +79,8 @@ def main() -> None:
             "Small sizes are latency-bound (a one-way flag over NVLink costs ~2 us, a launch ~3 us): the floor measured",
             "here is ~12-13 us for the one-shot kernels vs ~19 us for `ncclAllReduce`.  The fused bucket kernel also",
             "reads the scattered gradients and writes them back (two extra HBM passes that stock DDP does in separate",
-            "copy kernels), so at 64 MB+ it trails the in-place kernels; DDP buckets are <= 25 MB, where it is ahead of",
-            "NCCL, and large fp32 payloads are the round-2 item in `docs/ROADMAP.md`.", ""]
+            "copy kernels), so at 64 MB+ with an fp32 wire it trails NCCL; DDP buckets are <= 29 MB, where it is ahead, and the",
+            "in-place symmetric-memory kernel (no staging passes) is ahead of NCCL at every size from 1 KB to 1 GB at 8 GPUs.", ""]
     for w in sorted(latest):
         body.append(table(latest[w]))
     body += DDP_SECTION.strip("\n").split("\n")
