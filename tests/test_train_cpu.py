@@ -100,6 +100,25 @@ def test_torchrun_gloo_two_ranks(tmp_path, free_port):
     assert "backend='gloo'" in res.stdout and "world_size=2" in res.stdout
 
 
+def test_launch_scripts_run_the_template(tmp_path, free_port):
+    """The shipped launchers themselves (reference: run.sh, run.slurm.sh - L5 of the layer map): `run.sh` with two ranks on
+    the CPU (gloo), and the per-node half of the SLURM launcher under a faked one-node SLURM environment."""
+    common = ["--no_cuda", "--no_tensorboard", "--max_steps", "6", "--save_steps", "6", "--logging_steps", "3", "--dataset_size", "256"]
+    env = dict(os.environ, OMP_NUM_THREADS="1", NGPU="2", MASTER_PORT=str(free_port))
+    res = subprocess.run(["sh", os.path.join(ROOT, "run.sh"), *common, "--output_dir", str(tmp_path / "a")], capture_output=True, text=True,
+                         timeout=240, env=env, cwd=ROOT)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "[Finished training.] [global_step=7]" in res.stdout and "world_size=2" in res.stdout
+    assert os.listdir(tmp_path / "a") == ["checkpoint-6"]
+    env = dict(os.environ, OMP_NUM_THREADS="1", SLURM_JOB_NUM_NODES="1", SLURM_NODEID="0", GPUS_PER_NODE="2", MASTER_ADDR="127.0.0.1",
+               MASTER_PORT=str(free_port), B200DDP_BACKEND="gloo")
+    res = subprocess.run(["bash", os.path.join(ROOT, "run.slurm.sh"), *common, "--output_dir", str(tmp_path / "b")], capture_output=True, text=True,
+                         timeout=240, env=env, cwd=ROOT)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "[Finished training.] [global_step=7]" in res.stdout and "backend='gloo'" in res.stdout
+    assert os.listdir(tmp_path / "b") == ["checkpoint-6"]
+
+
 def test_default_loss_and_dataset_per_model():
     import argparse
     from b200ddp.engine.trainer import build_criterion, build_dataset, loss_kind
