@@ -215,3 +215,17 @@ def test_bert_tiny_gpu_matches_cpu_reference():
         rel = float((p.grad.float().cpu() - q.grad).norm() / (q.grad.norm() + 1e-8))
         worst = max(worst, rel)
         assert rel < 0.15, (n, rel)
+
+
+def test_normalize_pads_channels_with_zeros():
+    """normalize_to_channels_last may write into a destination with more channels than the source: the extra ones are zeros."""
+    from b200ddp import _ext
+    C = _ext.get()
+    x = torch.randn(4, 3, 32, 40, device="cuda")
+    mean = torch.tensor([0.1, 0.2, 0.3], device="cuda")
+    istd = torch.tensor([2.0, 0.5, 1.5], device="cuda")
+    dst = torch.full((4, 8, 32, 40), 7.0, device="cuda", dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    C.normalize_to_channels_last(x, dst, mean, istd, 1.0)
+    ref = ((x - mean.view(1, 3, 1, 1)) * istd.view(1, 3, 1, 1)).to(torch.bfloat16)
+    assert torch.allclose(dst[:, :3].float(), ref.float(), atol=1e-2, rtol=1e-2)
+    assert float(dst[:, 3:].abs().max()) == 0.0
