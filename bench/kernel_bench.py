@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Per-kernel timings against the measured roofline (MEASURED_PEAKS.json: HBM copy GB/s, cuBLAS bf16 TFLOP/s).
 
-  python bench/kernel_bench.py [--only gemm,sgd,ln,xent,mse,input] [--out gpurun_out/kernels.json] [--iters 20]
+  python bench/kernel_bench.py [--only gemm,conv,bn,sgd,ln,xent,mse,input] [--out gpurun_out/kernels.json] [--iters 20]
 
 Timing hygiene (B200_PROFILING.md): >= 3 warm-up launches, CUDA events on the launching stream, a 256 MB write
 between timed launches to flush the 126 MB L2, median of `iters`.  Each entry reports algorithmic bytes / FLOPs,
@@ -53,7 +53,7 @@ def timeit(fn, iters=20, flush=True):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", type=str, default="gemm,bn,sgd,ln,xent,mse,input,h2d")
+    ap.add_argument("--only", type=str, default="gemm,conv,bn,sgd,ln,xent,mse,input,h2d")
     ap.add_argument("--out", type=str, default=None)
     ap.add_argument("--iters", type=int, default=20)
     args = ap.parse_args()
@@ -123,6 +123,37 @@ def main():
         ms = timeit(lambda: C.gemm(x, w, bias, False, False, 3, False, None), args.iters)
         lib = timeit(lambda: torch.nn.functional.gelu(torch.nn.functional.linear(x, w, bias)), args.iters)
         record(f"gemm+bias+gelu {M}x{N}x{K}", ms, flops=2.0 * M * N * K, lib_ms=lib, note="lib = cuBLAS linear + gelu kernel")
+
+    if "conv" in want:
+        import torch.nn.functional as F
+        torch.backends.cudnn.benchmark = True
+        n = 32
+        # the stem (default ON) and one layer of each kind of the stride-1 set (default OFF); full table: bench/conv_layers.py
+        x = torch.randn(n, 3, 224, 224, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        wt = (torch.randn(64, 3, 7, 7, device=dev) / 147 ** 0.5).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        dy = torch.randn(n, 64, 112, 112, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        xp = C.stem_pack_input(x)
+        fl = 2.0 * n * 112 * 112 * 64 * 147
+        lib = timeit(lambda: F.conv2d(x, wt, None, 2, 3), args.iters)
+        record("stem 7x7s2 fprop (pack + tcgen05 tap-GEMM) b32", timeit(lambda: C.stem_conv_fprop(x, wt, False, True), args.iters), flops=fl, lib_ms=lib)
+        lib = timeit(lambda: torch.ops.aten.convolution_backward(dy, x, wt, None, [2, 2], [3, 3], [1, 1], False, [0, 0], 1, [False, True, False]), args.iters)
+        record("stem 7x7s2 wgrad (split-pixel tcgen05 + reduce) b32", timeit(lambda: C.stem_conv_wgrad(dy, xp, 224, 224, 0), args.iters), flops=fl, lib_ms=lib)
+        for (ci, co, k, hw) in [(64, 256, 1, 56), (256, 64, 1, 56), (64, 64, 3, 56), (128, 128, 3, 28), (256, 1024, 1, 14), (512, 512, 3, 7)]:
+            pad = k // 2
+            xa = torch.randn(n, ci, hw, hw, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            wa = (torch.randn(co, ci, k, k, device=dev) / (ci * k * k) ** 0.5).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            da = torch.randn(n, co, hw, hw, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            fl = 2.0 * n * hw * hw * ci * co * k * k
+            tag = f"{k}x{k} {ci}->{co} @{hw}"
+
+            def bwd(mask):
+                return torch.ops.aten.convolution_backward(da, xa, wa, None, [1, 1], [pad, pad], [1, 1], False, [0, 0], 1, mask)
+            record(f"conv fprop {tag}", timeit(lambda: C.conv_fprop(xa, wa, 1, pad, -1, 0, 0, False), args.iters), flops=fl,
+                   lib_ms=timeit(lambda: F.conv2d(xa, wa, None, 1, pad), args.iters))
+            record(f"conv dgrad {tag}", timeit(lambda: C.conv_dgrad(da, wa, 1, pad, -1, 0, 0), args.iters), flops=fl,
+                   lib_ms=timeit(lambda: bwd([True, False, False]), args.iters))
+            record(f"conv wgrad {tag}", timeit(lambda: C.conv_wgrad(da, xa, k, 1, pad, 0, 0, 0), args.iters), flops=fl,
+                   lib_ms=timeit(lambda: bwd([False, True, False]), args.iters))
 
     if "bn" in want:
         from b200ddp.ops import FusedBatchNormAct2d
