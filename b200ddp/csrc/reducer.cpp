@@ -193,7 +193,6 @@ void Reducer::launch_bucket(int b, cudaStream_t compute) {
   ctx.pad_off = (size_t)(2 + b) * kPadSetBytes;
   static const int debug_mode = [] { const char* e = std::getenv("B200DDP_DEBUG_BUCKET"); return e ? std::atoi(e) : 0; }();
   if (debug_mode == 1) { s.launched = true; ++launches; if (mark) nvtxRangePop(); return; }                 // diagnostics: bookkeeping only
-  if (debug_mode == 2) { B200_CUDA_CHECK(cudaMemsetAsync(arena_->error_word_dev() + 0, 0, 0, where)); }   // (no-op placeholder)
   launch_bucket_allreduce(ctx, s.table, s.stage_off, (DType)plans_[b].grad_dtype, (DType)plans_[b].wire_dtype, s.algo, blocks,
                           (opt_.as_view || opt_.find_unused) ? s.flat_out : nullptr, sq,
                           opt_.find_unused ? s.flags_dev : nullptr, scale, scatter, where);

@@ -80,7 +80,10 @@ class ResNet(nn.Module):
         return nn.Sequential(*mods)
 
     def forward(self, x):
-        y, part = self.conv1.forward_with_stats(x)           # BatchNorm statistics ride on the stem's epilogue
+        if self.training:
+            y, part = self.conv1.forward_with_stats(x)       # BatchNorm statistics ride on the stem's epilogue
+        else:
+            y, part = self.conv1(x), None                    # inference normalises with the running statistics
         x = self.maxpool(self.bn1(y, partials=part))
         x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
         x = torch.flatten(self.avgpool(x), 1)
