@@ -1,12 +1,11 @@
 """Grouped tile rasterisation (B200DDP_GEMM_GROUP_M / set_gemm_group_m): results must be bit-identical to the
-default m-fastest order, since only the order in which persistent CTAs pick tiles changes."""
-import os
+default m-fastest order, since only the order in which persistent CTAs pick tiles changes.  (Measured: not faster on any
+benchmarked shape - 8192^3 0.88 vs 0.72 ms - so the default stays m-fastest; the knob remains for larger-than-L2 problems.)"""
 
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("B200DDP_TEST_OPTIN") != "1",
-                                                   reason="written after the last GPU session: run with B200DDP_TEST_OPTIN=1 (tools/round2_ablation.sh)")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("mode", [1, 2])
