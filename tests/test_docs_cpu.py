@@ -3,7 +3,8 @@ import os
 import re
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-DOCS = ["README.md", "DESIGN.md", "docs/INVENTORY.md", "docs/MIGRATING.md", "profiles/README.md"]
+DOCS = ["README.md", "DESIGN.md", "BASELINE.md", "docs/INVENTORY.md", "docs/MIGRATING.md", "docs/ROUND2.md", "profiles/README.md", "profiles/stem.md",
+        "profiles/conv_layers.md", "profiles/ddp_timeline_r2.md", "profiles/graph_replay_modes.md", "tools/README.md"]
 
 
 def _read(rel):
