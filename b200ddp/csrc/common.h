@@ -28,6 +28,18 @@ inline std::atomic<long long>& launch_counter() {
 }
 #define B200_COUNT_LAUNCH(n) ::b200::launch_counter().fetch_add((n), std::memory_order_relaxed)
 
+// Function attributes are per DEVICE: a process that drives several GPUs (the single-process DataParallel mode) must raise the
+// dynamic shared-memory limit of a kernel once on each of them.  `done` is a per-call-site bit mask over device ordinals.
+template <typename Kernel>
+inline void ensure_max_dynamic_smem(Kernel kernel, int bytes, std::atomic<unsigned long long>& done) {
+  int dev = 0;
+  B200_CUDA_CHECK(cudaGetDevice(&dev));
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (done.load(std::memory_order_acquire) & bit) return;
+  B200_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done.fetch_or(bit, std::memory_order_release);
+}
+
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74
 constexpr int kWarp = 32;
 

@@ -704,11 +704,8 @@ void launch_variant(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensor
   }
   const int smem = p.s_stages * p.s_stage_bytes + p.b_stages * p.b_slot_bytes + kStagingBytes + kBarrierBytes + 1024 + (EPI != 0 ? kStatsScratchBytes : 0);
   auto kernel = conv_tap_gemm_kernel<BLOCK_N, B_MN, EPI>;
-  static bool configured = false;
-  if (!configured) {
-    B200_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
-  }
+  static std::atomic<unsigned long long> configured{0};
+  ensure_max_dynamic_smem(kernel, 227 * 1024, configured);
   const int grid = conv_grid_size(p.num_m_tiles, p.num_n_tiles, EPI != 0);
   kernel<<<grid, kThreads, smem, stream>>>(ma, mb, md, p);
   B200_CUDA_CHECK(cudaGetLastError()); B200_COUNT_LAUNCH(1);

@@ -359,11 +359,8 @@ void launch_conv_wgrad(const void* dy, const void* x, void* dw, int N, int H, in
     uint64_t xs[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
     mx = conv_encode_map(x, 4, xd, xs, bx);
   }
-  static bool configured = false;
-  if (!configured) {
-    B200_CUDA_CHECK(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
-  }
+  static std::atomic<unsigned long long> configured{0};
+  ensure_max_dynamic_smem(conv_wgrad_kernel, 227 * 1024, configured);
   conv_wgrad_kernel<<<pl.grid, kThreads, pl.smem, stream>>>(mdy, mx, p);
   B200_CUDA_CHECK(cudaGetLastError());
   const size_t n = (size_t)Cout * R * S * Cin;
@@ -600,22 +597,16 @@ void launch_stem_conv_wgrad(const void* dy, const void* xp, void* dw2, int N, in
     if (!stem_generic_plan(N, H, W, Cout, &pl)) throw std::runtime_error("stem wgrad: unsupported geometry");
     WgradParams p = pl.p;
     p.partial = workspace;
-    static bool configured = false;
-    if (!configured) {
-      B200_CUDA_CHECK(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      configured = true;
-    }
+    static std::atomic<unsigned long long> configured{0};
+    ensure_max_dynamic_smem(conv_wgrad_kernel, 227 * 1024, configured);
     conv_wgrad_kernel<<<pl.grid, kThreads, pl.smem, stream>>>(mdy, mx, p);
     split = p.split;
   } else {
     StemWgradParams p; int smem;
     if (!stem_dedicated_plan(N, H, W, Cout, &p, &smem)) throw std::runtime_error("stem wgrad: unsupported geometry");
     p.partial = workspace;
-    static bool configured = false;
-    if (!configured) {
-      B200_CUDA_CHECK(cudaFuncSetAttribute(stem_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      configured = true;
-    }
+    static std::atomic<unsigned long long> configured{0};
+    ensure_max_dynamic_smem(stem_wgrad_kernel, 227 * 1024, configured);
     stem_wgrad_kernel<<<p.split, kThreads, smem, stream>>>(mx, mdy, p);
     split = p.split;
   }

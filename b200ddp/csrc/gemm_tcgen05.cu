@@ -598,11 +598,8 @@ void launch_variant(const void* a, const void* b, const GemmParams& p, cudaStrea
   CUtensorMap map_b = B_MN ? make_map(b, p.K, p.N, BLOCK_K, 64) : make_map(b, p.N, p.K, BLOCK_N, BLOCK_K);
   CUtensorMap map_d = TMA_ST ? make_map(p.d, p.M, p.N, 32, 64) : map_a;       // unused by the direct epilogue
   auto kernel = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN, TMA_ST, STATS>;
-  static bool configured = false;
-  if (!configured) {
-    B200_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    configured = true;
-  }
+  static std::atomic<unsigned long long> configured{0};
+  ensure_max_dynamic_smem(kernel, kSmem, configured);
   const int tiles = ceil_div(p.M, BLOCK_M) * ceil_div(p.N, BLOCK_N);
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
   kernel<<<grid, kNumThreads, kSmem, stream>>>(map_a, map_b, map_d, p);
@@ -618,11 +615,8 @@ void launch_variant_2cta(const void* a, const void* b, const GemmParams& p, cuda
   CUtensorMap map_b = B_MN ? make_map(b, p.K, p.N, BLOCK_K, 64) : make_map(b, p.N, p.K, L::BN / 2, BLOCK_K);
   CUtensorMap map_d = TMA_ST ? make_map(p.d, p.M, p.N, 32, 64) : map_a;
   auto kernel = gemm_bf16_2cta_kernel<A_MN, B_MN, TMA_ST, STATS>;
-  static bool configured = false;
-  if (!configured) {
-    B200_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    configured = true;
-  }
+  static std::atomic<unsigned long long> configured{0};
+  ensure_max_dynamic_smem(kernel, kSmem, configured);
   const int tiles = ceil_div(p.M, 2 * BLOCK_M) * ceil_div(p.N, L::BN);
   const int pairs = tiles < kNumSMs / 2 ? tiles : kNumSMs / 2;
   kernel<<<2 * pairs, kNumThreads, kSmem, stream>>>(map_a, map_b, map_d, p);     // __cluster_dims__(2,1,1) on the kernel

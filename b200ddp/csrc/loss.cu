@@ -233,12 +233,9 @@ void launch_xent_fwd_bwd(const void* logits, const long long* targets, DType dt,
   if (smem <= 200 * 1024 && ((reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(dlogits)) % esz) == 0 &&
       (reinterpret_cast<uintptr_t>(logits) & 15u) == (reinterpret_cast<uintptr_t>(dlogits) & 15u)) {
     // dlogits rows must share the 16-byte phase of the logits rows (both come from the same allocator: they do)
-    static bool configured = false;
-    if (!configured) {
-      B200_CUDA_CHECK(cudaFuncSetAttribute(xent_fwd_bwd_smem_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      B200_CUDA_CHECK(cudaFuncSetAttribute(xent_fwd_bwd_smem_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      configured = true;
-    }
+    static std::atomic<unsigned long long> configured_bf16{0}, configured_f32{0};
+    ensure_max_dynamic_smem(xent_fwd_bwd_smem_kernel<__nv_bfloat16>, 200 * 1024, configured_bf16);
+    ensure_max_dynamic_smem(xent_fwd_bwd_smem_kernel<float>, 200 * 1024, configured_f32);
     if (dt == DType::BF16)
       xent_fwd_bwd_smem_kernel<__nv_bfloat16><<<rows, kLossThreads, smem, s>>>((const __nv_bfloat16*)logits, targets, rows, cols, ignore_index, g,
                                                                              row_loss, (__nv_bfloat16*)dlogits);
