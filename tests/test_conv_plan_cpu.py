@@ -170,3 +170,20 @@ def test_stem_window_algebra_and_geometry():
     d = dw2.reshape(k, 4, 8, 2, 4)                               # [co, t, p, half, c]
     dw = torch.stack([d[:, r // 2, 1:8, r % 2, :3] for r in range(7)], dim=1).permute(0, 3, 1, 2)   # [co, c, r, s]
     assert torch.allclose(dw, wg.grad, atol=2e-3, rtol=1e-4)
+
+
+def test_conv_modules_fall_back_to_stock_on_cpu_and_keep_stock_state_dicts():
+    """StemConv7x7 / PointwiseConv2d / Conv3x3 are nn.Conv2d subclasses: same parameter names and shapes (checkpoints and DDP
+    bucket layouts are unchanged), stock computation on CPU, and no epilogue statistics there."""
+    import torch
+    import torch.nn as nn
+    from b200ddp.ops import Conv3x3, PointwiseConv2d, StemConv7x7
+    torch.manual_seed(0)
+    for ours, stock, x in ((StemConv7x7(), nn.Conv2d(3, 64, 7, 2, 3, bias=False), torch.randn(2, 3, 32, 32)),
+                           (PointwiseConv2d(64, 128), nn.Conv2d(64, 128, 1, bias=False), torch.randn(2, 64, 8, 8)),
+                           (Conv3x3(64, 64, stride=2), nn.Conv2d(64, 64, 3, 2, 1, bias=False), torch.randn(2, 64, 8, 8))):
+        assert list(ours.state_dict().keys()) == list(stock.state_dict().keys()) == ["weight"]
+        stock.load_state_dict(ours.state_dict())
+        y, part = ours.forward_with_stats(x)
+        assert part is None and torch.allclose(y, stock(x), atol=1e-6)
+        assert torch.allclose(ours(x), stock(x), atol=1e-6)
