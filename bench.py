@@ -162,7 +162,9 @@ def opt_ins(model):
     """Non-default kernel choices switched on through the environment (none by default) - recorded so a run is
     reproducible from its JSON line."""
     out = {}
-    for key in ("B200DDP_GEMM_GROUP_M", "B200DDP_GEMM_TMA_STORE", "B200DDP_GEMM_CTAS", "B200DDP_CONV", "B200DDP_CONV_WGRAD", "B200DDP_DISABLE_TC"):
+    for key in ("B200DDP_GEMM_GROUP_M", "B200DDP_GEMM_TMA_STORE", "B200DDP_GEMM_CTAS", "B200DDP_CONV", "B200DDP_CONV_WGRAD", "B200DDP_DISABLE_TC",
+                "B200DDP_STEM", "B200DDP_STEM_WGRAD", "B200DDP_STEM_RESIDENT", "B200DDP_BLOCK_FUSE", "B200DDP_PDL", "B200DDP_BN_FUSED", "B200DDP_DDP_SERIAL",
+                "B200DDP_COMM_BLOCKS", "B200DDP_TAIL_BLOCKS", "B200DDP_TAIL_BUCKET_MB", "B200DDP_TAIL_ONE_SHOT_MAX_MB"):
         if os.environ.get(key):
             out[key] = os.environ[key]
     return {"opt_in": out} if out else {}
